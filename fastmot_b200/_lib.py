@@ -1,0 +1,88 @@
+"""ctypes binding of libfastmot_b200.so (include/fastmot_b200.h).
+
+There is no CPU fallback: if the shared library is missing or the device is not a B200 the product
+classes raise.  Loading the library (dlopen + symbol lookup) needs no GPU; running any op does.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfastmot_b200.so")
+
+c_p = C.c_void_p
+c_i = C.c_int
+c_d = C.c_double
+c_f = C.c_float
+c_ll = C.c_longlong
+
+
+class FmKalmanParams(C.Structure):
+    _fields_ = [("trans_mat", c_d * 64), ("acc_cov", c_d * 64),
+                ("std_factor_acc", c_d), ("std_offset_acc", c_d),
+                ("std_factor_det", c_d * 2), ("std_factor_klt", c_d * 2),
+                ("min_std_det", c_d * 2), ("min_std_klt", c_d * 2),
+                ("init_pos_weight", c_d), ("init_vel_weight", c_d)]
+
+
+# name -> (restype, argtypes); kept in one table so tests can check it against the header
+SIGNATURES = {
+    "fm_last_error": (C.c_char_p, []),
+    "fm_version": (c_i, []),
+    "fm_device_ok": (c_i, []),
+    "fm_memcpy_async": (c_i, [c_p, c_p, c_ll, c_p]),
+    "fm_kalman_step_batched": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p,
+                                      C.POINTER(FmKalmanParams), c_d, c_d, c_p, c_p, c_p]),
+    "fm_kalman_create_batched": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, C.POINTER(FmKalmanParams), c_p]),
+    "fm_motion_distance": (c_i, [c_p, c_p, c_p, c_i, c_p, c_i, C.POINTER(FmKalmanParams), c_p, c_p]),
+    "fm_matching_cost": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i,
+                               c_d, c_d, c_d, C.POINTER(FmKalmanParams), c_p, c_p]),
+    "fm_feature_update": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p]),
+    "fm_iou_cost": (c_i, [c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_i, c_d, c_p, c_p]),
+    "fm_find_occluded": (c_i, [c_p, c_i, c_d, c_p, c_p]),
+    "fm_lsa_workspace_bytes": (c_ll, [c_i, c_i]),
+    "fm_lsa": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_p]),
+    "fm_greedy_match": (c_i, [c_p, c_i, c_i, c_d, c_p, c_p, c_p]),
+}
+
+
+class FastMOTLibError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """dlopen the library and bind every symbol of the header. Raises if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FastMOTLibError(
+            f"{LIB_PATH} not found: build it with `python -m fastmot_b200.build` "
+            "(there is no CPU fallback for the fastmot_b200 hot path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise FastMOTLibError(f"symbol {name} missing from {LIB_PATH}") from e
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().fm_last_error().decode(errors="replace")
+        raise FastMOTLibError(f"{what} failed (code {rc}): {msg}")
+
+
+def require_device():
+    """Raise unless a B200-class device is usable (called by every product class constructor)."""
+    lib = load()
+    if not lib.fm_device_ok():
+        raise FastMOTLibError("fastmot_b200 needs an sm_100 (B200) CUDA device: "
+                              + lib.fm_last_error().decode(errors="replace"))
+    return lib

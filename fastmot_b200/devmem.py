@@ -1,0 +1,103 @@
+"""Device-memory plumbing: torch tensors are used only as containers (allocation, streams, pinned memory).
+
+`Uplink` packs many small host arrays into one pinned block and ships them with a single async H2D copy;
+`ptr()` turns tensors into raw addresses for the C-ABI.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+
+def ptr(t):
+    """Raw device (or pinned-host) address of a torch tensor, or None."""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(stream=None):
+    s = torch.cuda.current_stream() if stream is None else stream
+    return C.c_void_p(s.cuda_stream)
+
+
+class Uplink:
+    """Ring of pinned staging blocks -> one device block each; one cudaMemcpyAsync per `flush`."""
+
+    ALIGN = 256
+
+    def __init__(self, nbytes=1 << 20, depth=4, device="cuda"):
+        self.nbytes = nbytes
+        self.host = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in range(depth)]
+        self.host_np = [h.numpy() for h in self.host]
+        self.dev = [torch.empty(nbytes, dtype=torch.uint8, device=device) for _ in range(depth)]
+        self.events = [None] * depth
+        self.cur = 0
+        self.off = 0
+        self._begin()
+
+    def _begin(self):
+        ev = self.events[self.cur]
+        if ev is not None:
+            ev.synchronize()
+        self.off = 0
+
+    def put(self, arr):
+        """Stage a host ndarray; returns the device address (c_void_p) it will have after flush()."""
+        arr = np.ascontiguousarray(arr)
+        n = arr.nbytes
+        off = self.off
+        if off + n > self.nbytes:
+            raise MemoryError("Uplink block overflow")
+        if n:
+            self.host_np[self.cur][off:off + n] = arr.view(np.uint8).reshape(-1)
+        self.off = (off + n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        return C.c_void_p(self.dev[self.cur].data_ptr() + off)
+
+    def flush(self):
+        if self.off:
+            self.dev[self.cur][:self.off].copy_(self.host[self.cur][:self.off], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self.events[self.cur] = ev
+        self.cur = (self.cur + 1) % len(self.host)
+        self._begin()
+
+
+class Downlink:
+    """Device scratch block mirrored by a pinned host block; kernels write results at `alloc`ed offsets,
+    `fetch()` brings the used prefix back with one D2H copy + stream synchronize."""
+
+    ALIGN = 256
+
+    def __init__(self, nbytes=1 << 20, device="cuda"):
+        self.nbytes = nbytes
+        self.dev = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        self.host_np = self.host.numpy()
+        self.off = 0
+        self.items = []
+
+    def reset(self):
+        self.off = 0
+        self.items = []
+
+    def alloc(self, shape, dtype):
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        off = self.off
+        if off + n > self.nbytes:
+            raise MemoryError("Downlink block overflow")
+        self.off = (off + n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.items.append((off, n, tuple(shape), dtype))
+        return C.c_void_p(self.dev.data_ptr() + off), len(self.items) - 1
+
+    def fetch(self):
+        """Returns list of ndarrays (views into the pinned block — copy if kept across fetches)."""
+        if self.off:
+            self.host[:self.off].copy_(self.dev[:self.off], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        out = []
+        for off, n, shape, dtype in self.items:
+            out.append(self.host_np[off:off + n].view(dtype).reshape(shape))
+        return out

@@ -1,0 +1,125 @@
+/*
+ * fastmot_b200 — C-ABI of the B200-native FastMOT hot path (libfastmot_b200.so, sm_100a).
+ *
+ * The reference (GeekAlexis/FastMOT) is Python; its only native boundary is the TensorRT plugin
+ * "YoloLayer_TRT" (fastmot/plugins/yolo_layer.h:44-147) loaded with ctypes
+ * (fastmot/utils/inference.py:49-53).  This header is what the reference's Python stages bind instead
+ * (ctypes stubs in INTEGRATION.md).  Each entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name starts with `h_` (host) or says so;
+ *   - the caller owns all memory; kernels never allocate, never synchronise;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return 0 on success, non-zero error code otherwise (text via fm_last_error());
+ *   - boxes are inclusive-pixel tlbr doubles [x1,y1,x2,y2] as in fastmot/utils/rect.py.
+ */
+#ifndef FASTMOT_B200_H
+#define FASTMOT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- library ---------------------------------- */
+const char* fm_last_error(void);
+int fm_version(void);
+/* 1 if a CUDA device with compute capability 10.x is present and usable, else 0 (no kernels are run). */
+int fm_device_ok(void);
+/* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream) — lets the Python host move small blocks without
+ * another CUDA binding. */
+int fm_memcpy_async(void* dst, const void* src, long long bytes, void* stream);
+
+/* ---------------------------------------------------------------- Kalman filter ----------------------------- */
+/* Mirrors fastmot/kalman_filter.py:14-24 (ctor params) + :294-306 (_init_mat). */
+typedef struct FmKalmanParams {
+    double trans_mat[64];     /* A, row-major 8x8 */
+    double acc_cov[64];       /* Q0, row-major 8x8 */
+    double std_factor_acc, std_offset_acc;
+    double std_factor_det[2], std_factor_klt[2];
+    double min_std_det[2], min_std_klt[2];
+    double init_pos_weight, init_vel_weight;
+} FmKalmanParams;
+
+#define FM_KF_WARP 1      /* kalman_filter.py:227-292 */
+#define FM_KF_PREDICT 2   /* kalman_filter.py:128-147, 308-319 */
+#define FM_KF_UPDATE 4    /* kalman_filter.py:180-204, 321-345 */
+#define FM_KF_MEAS_DET 8  /* measurement noise of MeasType.DETECTOR, else MeasType.FLOW */
+#define FM_KF_MEAS_BY_SLOT 16 /* meas / has_meas are slot-indexed pools instead of per-item arrays */
+
+/* One launch for the whole track set; replaces the per-track loop of tracker.py:164-183 (flags
+ * WARP|PREDICT|UPDATE, FLOW noise, multiplier = mult_num[i] / mult_den_pool[slot]) and of tracker.py:262-274
+ * (flags UPDATE|MEAS_DET).  State lives in slot-indexed pools mean_pool[cap][8], cov_pool[cap][64].
+ * slots[n] selects the tracks; meas[n][4], has_meas[n] (NULL = all), mult_num[n] (NULL = 1).
+ * h_ok: optional device flag; if *h_ok == 0 the launch is a no-op (flow failed, tracker.py:160-162).
+ * out_tlbr[n][4] = round-half-even(mean[:4]) (rect.py:5-12), also stored to tlbr_pool[slot] when non-NULL;
+ * out_lost[n] = ios(box, frame) < 0.5 (tracker.py:179). */
+int fm_kalman_step_batched(double* mean_pool, double* cov_pool, double* tlbr_pool, const int* slots, int n, int flags,
+                           const double* homography, const int* h_ok, const double* meas,
+                           const unsigned char* has_meas, const double* mult_num, const double* mult_den_pool,
+                           const FmKalmanParams* h_params, double frame_w, double frame_h, double* out_tlbr,
+                           unsigned char* out_lost, void* stream);
+
+/* kalman_filter.py:96-126 for n detections at once; box i is tlbr[tlbr_idx ? tlbr_idx[i] : i]. */
+int fm_kalman_create_batched(double* mean_pool, double* cov_pool, double* tlbr_pool, const int* slots,
+                             const double* tlbr, const int* tlbr_idx, int n, const FmKalmanParams* h_params,
+                             void* stream);
+
+/* kalman_filter.py:206-225: out[n_trk][n_det] squared Mahalanobis distances (slots NULL = identity). */
+int fm_motion_distance(const double* mean_pool, const double* cov_pool, const int* slots, int n_trk,
+                       const double* det_tlbr, int n_det, const FmKalmanParams* h_params, double* out, void* stream);
+
+/* ---------------------------------------------------------------- association ------------------------------ */
+#define FM_METRIC_EUCLIDEAN 0 /* fastmot/utils/distance.py:11-13 */
+#define FM_METRIC_COSINE 1
+#define FM_INF_COST 1e5       /* fastmot/utils/matching.py:7 */
+#define FM_CHI_SQ_INV_95 9.4877
+
+/* Fused replacement of MultiTracker._matching_cost (tracker.py:314-341):
+ *   cdist(features, embeddings, metric, empty_mask, fill) (distance.py:16-87)
+ *   + per-row Mahalanobis gating (kalman_filter.py:206-225, 347-353)
+ *   + fuse_motion (matching.py:100-106) + gate_cost (matching.py:109-116).
+ * feat_pool[cap][dim] f32 running-average features, feat_valid_pool[cap] (count > 0);
+ * trk_slots[n_trk], trk_labels[n_trk]; det_* arrays have n_det rows, det_sel[n_det] (NULL = identity) selects
+ * the rows of the full detection arrays that are still unmatched.  cost[n_trk][n_det] f64 row-major.
+ * motion_weight < 0 disables the motion term; max_cost < 0 disables the cost gate (tracker.py:355-366 re-ID). */
+int fm_matching_cost(const float* feat_pool, const unsigned char* feat_valid_pool, const double* mean_pool,
+                     const double* cov_pool, const int* trk_slots, const long long* trk_labels, int n_trk,
+                     const float* det_emb, const double* det_tlbr, const long long* det_labels,
+                     const unsigned char* det_occluded, const int* det_sel, int n_det, int dim, int metric,
+                     double fill_val, double motion_weight, double max_cost, const FmKalmanParams* h_params,
+                     double* cost, void* stream);
+
+/* AverageFeature.update / merge (fastmot/track.py:100-126) for n tracks at once.
+ * vec[.][dim] rows selected by vec_idx[n] (NULL = identity); counts[n] = the NEW count of each track
+ * (count == 1: sum = avg = vec; else sum += vec, avg = normalise(sum / count)).  Sets valid_pool[slot] = 1. */
+int fm_feature_update(float* sum_pool, float* avg_pool, float* last_pool, unsigned char* valid_pool, const int* slots,
+                      const float* vec, const int* vec_idx, const int* counts, int n, int dim, void* stream);
+
+/* iou_dist (distance.py:90-108) + gate_cost (matching.py:109-116); boxes gathered by index lists.
+ * trk_tlbr_pool[cap][4]; labels may be NULL (no label gate), max_cost < 0 disables the cost gate. */
+int fm_iou_cost(const double* trk_tlbr_pool, const int* trk_slots, const long long* trk_labels, int n_trk,
+                const double* det_tlbr, const long long* det_labels, const int* det_sel, int n_det,
+                double max_cost, double* cost, void* stream);
+
+/* find_occluded (rect.py:142-157): out[i] = any j != i with inter(i,j)/area(i) >= thresh. */
+int fm_find_occluded(const double* tlbr, int n, double thresh, unsigned char* out, void* stream);
+
+/* scipy.optimize.linear_sum_assignment (SciPy 1.18.1 rectangular_lsap.cpp, shortest augmenting path;
+ * call site matching.py:27) — bit-exact replay of its scan order and tie rules, one warp.
+ * cost[nr][nc] f64 row-major.  col4row[nr]: assigned column, -1 if the row is unassigned, and
+ * (-2 - col) if assigned but cost >= FM_INF_COST (demoted by matching.py:64-69).  Returns FM_ERR_ARG via
+ * status[0] = 1 if the matrix is infeasible.  workspace: >= fm_lsa_workspace_bytes(nr, nc). */
+long long fm_lsa_workspace_bytes(int nr, int nc);
+int fm_lsa(const double* cost, int nr, int nc, int* col4row, int* status, void* workspace, void* stream);
+
+/* _greedy_match (matching.py:73-97): repeated global argmin <= max_cost with row/column removal.
+ * col4row[nr] = matched column or -1; match_order[nr] = rank of the match in discovery order or -1. */
+int fm_greedy_match(const double* cost, int nr, int nc, double max_cost, int* col4row, int* match_order,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTMOT_B200_H */
