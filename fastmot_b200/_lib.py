@@ -24,12 +24,17 @@ class FmKalmanParams(C.Structure):
                 ("init_pos_weight", c_d), ("init_vel_weight", c_d)]
 
 
+class FmYoloHead(C.Structure):
+    _fields_ = [("anchors", c_f * 12), ("scale_x_y", c_f)]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check it against the header
 SIGNATURES = {
     "fm_last_error": (C.c_char_p, []),
     "fm_version": (c_i, []),
     "fm_device_ok": (c_i, []),
     "fm_memcpy_async": (c_i, [c_p, c_p, c_ll, c_p]),
+    "fm_host_is_pinned": (c_i, [c_p]),
     "fm_kalman_step_batched": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p,
                                       C.POINTER(FmKalmanParams), c_d, c_d, c_p, c_p, c_p]),
     "fm_kalman_create_batched": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, C.POINTER(FmKalmanParams), c_p]),
@@ -42,6 +47,12 @@ SIGNATURES = {
     "fm_lsa_workspace_bytes": (c_ll, [c_i, c_i]),
     "fm_lsa": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_p]),
     "fm_greedy_match": (c_i, [c_p, c_i, c_i, c_d, c_p, c_p, c_p]),
+    "fm_letterbox_preproc": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
+    "fm_roi_resize_norm": (c_i, [c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
+    "fm_yolo_decode_filter": (c_i, [c_p, c_i, c_i, c_i, c_i, C.POINTER(FmYoloHead), c_i, c_i, c_i, c_i, c_i, c_p,
+                                     c_d, c_f, c_f, c_f, c_f, c_p, c_p, c_p, c_i, c_p]),
+    "fm_nms_mask_bytes": (c_ll, [c_i]),
+    "fm_diou_nms_filter": (c_i, [c_p, c_p, c_p, c_i, c_d, c_d, c_d, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
 }
 
 

@@ -41,3 +41,13 @@ extern "C" int fm_memcpy_async(void* dst, const void* src, long long bytes, void
     }
     return FM_OK;
 }
+
+extern "C" int fm_host_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return a.type == cudaMemoryTypeHost ? 1 : 0;
+}

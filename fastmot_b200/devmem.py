@@ -101,3 +101,39 @@ class Downlink:
         for off, n, shape, dtype in self.items:
             out.append(self.host_np[off:off + n].view(dtype).reshape(shape))
         return out
+
+
+class FrameUploader:
+    """HxWx3 u8 host frame -> device tensor with one async copy.  Page-locked sources (detected with
+    cudaPointerGetAttributes) are copied directly; pageable ones are staged through an internal pinned ring."""
+
+    def __init__(self, size, depth=2, device="cuda"):
+        from . import _lib
+        self._lib = _lib.load()
+        w, h = size
+        self.shape = (h, w, 3)
+        self.nbytes = h * w * 3
+        self.dev = [torch.empty(self.shape, dtype=torch.uint8, device=device) for _ in range(depth)]
+        self.host = [torch.empty(self.shape, dtype=torch.uint8).pin_memory() for _ in range(depth)]
+        self.host_np = [t.numpy() for t in self.host]
+        self.events = [None] * depth
+        self.cur = 0
+
+    def upload(self, frame):
+        frame = np.ascontiguousarray(frame)
+        if frame.shape != self.shape or frame.dtype != np.uint8:
+            raise ValueError(f"frame must be uint8 {self.shape}, got {frame.dtype} {frame.shape}")
+        k = self.cur
+        self.cur = (k + 1) % len(self.dev)
+        src = frame.ctypes.data
+        if not self._lib.fm_host_is_pinned(C.c_void_p(src)):
+            ev = self.events[k]
+            if ev is not None:
+                ev.synchronize()
+            np.copyto(self.host_np[k], frame)
+            src = self.host[k].data_ptr()
+        self._lib.fm_memcpy_async(C.c_void_p(self.dev[k].data_ptr()), C.c_void_p(src), self.nbytes, stream_ptr())
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[k] = ev
+        return self.dev[k]

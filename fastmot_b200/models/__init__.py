@@ -1,0 +1,3 @@
+from .yolo import YOLO
+from .reid import ReID
+from .label import set_label_map, get_label_name

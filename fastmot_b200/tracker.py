@@ -105,7 +105,8 @@ class MultiTracker:
         self.flow.bind_pool(self.pool)
         self.frame_rect = np.array([0., 0., size[0] - 1., size[1] - 1.])
 
-        self.up = Uplink(4 << 20)
+        self.up = Uplink(1 << 20, depth=8)        # per-stage id lists (many flushes per update)
+        self.up_det = Uplink(4 << 20, depth=2)    # detections of the current update (one flush per update)
         self.down = Downlink(1 << 20)
         dev = torch.device("cuda")
         self._cost = torch.empty(1 << 20, dtype=torch.float64, device=dev)   # up to 1024x1024
@@ -376,9 +377,9 @@ class MultiTracker:
         if dim != self.pool.feat_dim:
             raise ValueError(f"embedding dim {dim} != pool feat_dim {self.pool.feat_dim}")
         self._emb_keepalive = emb_t
-        p_tlbr = self.up.put(det_tlbr)
-        p_labels = self.up.put(det_label)
-        self.up.flush()
+        p_tlbr = self.up_det.put(det_tlbr)
+        p_labels = self.up_det.put(det_label)
+        self.up_det.flush()
         self.down.reset()
         occluded_det_mask = np.zeros(n_det, bool)
         occ_dev = torch.empty(max(n_det, 1), dtype=torch.uint8, device=dev)

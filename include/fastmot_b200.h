@@ -30,6 +30,8 @@ int fm_device_ok(void);
 /* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream) — lets the Python host move small blocks without
  * another CUDA binding. */
 int fm_memcpy_async(void* dst, const void* src, long long bytes, void* stream);
+/* 1 if the HOST pointer is page-locked (cudaHostAlloc / cudaHostRegister), else 0. */
+int fm_host_is_pinned(const void* h_ptr);
 
 /* ---------------------------------------------------------------- Kalman filter ----------------------------- */
 /* Mirrors fastmot/kalman_filter.py:14-24 (ctor params) + :294-306 (_init_mat). */
@@ -118,6 +120,48 @@ int fm_lsa(const double* cost, int nr, int nc, int* col4row, int* status, void* 
  * col4row[nr] = matched column or -1; match_order[nr] = rank of the match in discovery order or -1. */
 int fm_greedy_match(const double* cost, int nr, int nc, double max_cost, int* col4row, int* match_order,
                     void* stream);
+
+/* ---------------------------------------------------------------- detector pre/post-processing --------------- */
+#define FM_MAX_ANCHORS 6 /* fastmot/plugins/yolo_layer.h:11 */
+typedef struct FmYoloHead {
+    float anchors[2 * FM_MAX_ANCHORS]; /* (w,h) pairs in input pixels, fastmot/models/yolo.py:154-299 */
+    float scale_x_y;
+} FmYoloHead;
+
+/* YOLODetector._preprocess + _create_letterbox (fastmot/detector.py:289-320): bilinear resize of the BGR u8 HWC
+ * frame into the ROI [roi_x, roi_y, roi_w, roi_h] of a dst_w x dst_h network input (half-pixel centres, edge
+ * replicate, rounded to u8 like the reference's CuPy zoom), BGR->RGB, x/255; everything outside the ROI = 0.5.
+ * layout 0: fp32 planar CHW (the reference's TensorRT input); layout 1: fp16 NHWC, C padded to 4. */
+int fm_letterbox_preproc(const unsigned char* frame, int src_w, int src_h, int dst_w, int dst_h, int roi_x, int roi_y,
+                         int roi_w, int roi_h, int layout, void* out, void* stream);
+
+/* FeatureExtractor.extract_async preprocessing (fastmot/feature_extractor.py:48-60, 84-98; rect.py:92-97) for all
+ * crops in one launch: integer-truncated clamp crop, OpenCV INTER_LINEAR 8-bit fixed-point resize to
+ * out_w x out_h, BGR->RGB, (x/255 - mean)/std.  n = min(*n_dev, n_max) if n_dev != NULL else n_max.
+ * layout as above; output is [n][3][out_h][out_w] f32 or [n][out_h][out_w][4] f16. */
+int fm_roi_resize_norm(const unsigned char* frame, int src_w, int src_h, const double* tlbrs, const int* n_dev,
+                       int n_max, int out_w, int out_h, int layout, void* out, void* stream);
+
+/* CalDetection / CalDetection_NewCoords (fastmot/plugins/yolo_layer.cu:127-230) fused with the class mask +
+ * score threshold + pixel scaling of YOLODetector._filter_dets (fastmot/detector.py:331-341).  One call per
+ * head; head_out is [(5+C)*A, H, W] fp32 (is_fp16 = 0) or fp16.  Survivors write their 7-float record to
+ * dense[cand_base + idx][8] and append a sort key to keys[] (counter is incremented atomically; the caller zeroes
+ * it before the first head). */
+int fm_yolo_decode_filter(const void* head_out, int is_fp16, int yolo_w, int yolo_h, int num_anchors,
+                          const FmYoloHead* h_head, int num_classes, int input_w, int input_h, int new_coords,
+                          int cand_base, const unsigned char* label_mask, double conf_thresh, float size_w,
+                          float size_h, float off_x, float off_y, float* dense, unsigned long long* keys,
+                          int* counter, int key_cap, void* stream);
+
+/* Rest of _filter_dets (detector.py:343-365) + diou_nms (rect.py:198-244): sort by (class, objectness desc),
+ * per-class DIoU-NMS, to_tlbr rounding, area / aspect-ratio filters.  mask: >= fm_nms_mask_bytes(key_cap) bytes.
+ * Outputs (device): out_tlbr[max_out][4] f64, out_label[max_out] i64, out_conf[max_out] f64, out_count[1];
+ * status[0] = 1 if more than key_cap candidates passed the threshold (caller must raise). */
+long long fm_nms_mask_bytes(int key_cap);
+int fm_diou_nms_filter(unsigned long long* keys, const float* dense, const int* counter, int key_cap,
+                       double nms_thresh, double max_area, double min_aspect_ratio, unsigned long long* mask,
+                       int max_out, double* out_tlbr, long long* out_label, double* out_conf, int* out_count,
+                       int* status, void* stream);
 
 #ifdef __cplusplus
 }

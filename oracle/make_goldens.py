@@ -177,3 +177,36 @@ if __name__ == '__main__':
         sequence_golden('seq_T200.npz', dict(n_objects=200, seed=0), 32)
     if 'seqovl' in which:
         sequence_golden('seq_T70_overlap.npz', dict(n_objects=70, seed=5, overlap=True), 27)
+
+
+def detect_golden():
+    """_filter_dets (detector.py:322-365) known answers from the reference's own Numba function."""
+    fm = load_reference()
+    rng = np.random.default_rng(21)
+    rec = {}
+    cases = [(2500, False, (1920, 1920), (0., 420.)), (1200, True, (1920, 1080), (0., 0.)),
+             (6000, False, (1920, 1920), (0., 420.))]
+    for k, (K, two_cls, size, off) in enumerate(cases):
+        det = np.zeros((K, 7), np.float32)
+        det[:, :2] = rng.uniform(0, 0.9, (K, 2))
+        det[:, 2:4] = rng.uniform(0.01, 0.15, (K, 2)) * [1, 2.2]
+        det[:, 4] = rng.uniform(0, 1, K)
+        det[:, 5] = rng.integers(0, 2, K) if two_cls else 0
+        det[:, 6] = rng.uniform(0.2, 1, K)
+        lm = np.array([True, True]) if two_cls else np.array([True])
+        ref = fm.detector.YOLODetector._filter_dets(det.copy(), np.array(size), np.array(off), lm, 0.25, 0.5,
+                                                    800000, 1.2)
+        rec[f'det_{k}'] = det
+        rec[f'size_{k}'] = np.array(size)
+        rec[f'off_{k}'] = np.array(off)
+        rec[f'lm_{k}'] = lm
+        rec[f'tlbr_{k}'] = np.array([r[0] for r in ref]).reshape(-1, 4)
+        rec[f'label_{k}'] = np.array([r[1] for r in ref], np.int64)
+        rec[f'conf_{k}'] = np.array([r[2] for r in ref], np.float64)
+        print('detect case', k, K, '->', len(ref))
+    rec['n'] = np.int64(len(cases))
+    np.savez_compressed(os.path.join(OUT, 'detect_filter.npz'), **rec)
+
+
+if __name__ == '__main__' and 'detect' in (sys.argv[1:] or ['detect']):
+    detect_golden()

@@ -48,3 +48,16 @@ def run_greedy(cost, max_cost):
     order = torch.full((max(nr, 1),), -7, dtype=torch.int32, device=DEV)
     _lib.check(lib.fm_greedy_match(ptr(c), nr, nc, float(max_cost), ptr(out), ptr(order), stream_ptr()), "greedy")
     return host(out)[:nr], host(order)[:nr]
+
+
+class Keep:
+    """Uploads arrays and keeps the tensors alive until the object dies (a bare ptr(dev(x)) would free
+    the tensor before the kernel runs)."""
+
+    def __init__(self):
+        self.held = []
+
+    def __call__(self, a, dtype=None):
+        t = dev(a, dtype)
+        self.held.append(t)
+        return ptr(t)

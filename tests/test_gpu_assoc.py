@@ -86,7 +86,7 @@ def test_kalman_numpy_api_matches_oracle(prim):
 
 @pytest.mark.parametrize("metric", ["cosine", "euclidean"])
 def test_matching_cost_fused(prim, lib, metric):
-    from gpu_util import dev, host, kalman_params
+    from gpu_util import dev, host, kalman_params, Keep
     from fastmot_b200 import _lib
     from fastmot_b200.devmem import ptr, stream_ptr
     from oracle import assoc
@@ -110,9 +110,10 @@ def test_matching_cost_fused(prim, lib, metric):
     c = assoc.gate_cost(c, tl, dl[sel], 0.8)
     out = torch.zeros(nt, len(sel), dtype=torch.float64, device="cuda")
     slots = dev(np.arange(nt, dtype=np.int32))
-    rc = lib.fm_matching_cost(ptr(dev(XA)), ptr(dev(valid.astype(np.uint8))), ptr(dev(mean)),
-                              ptr(dev(cov.reshape(nt, 64))), ptr(slots), ptr(dev(tl)), nt, ptr(dev(XB)),
-                              ptr(dev(det_tlbr)), ptr(dev(dl)), ptr(dev(occ.astype(np.uint8))), ptr(dev(sel)),
+    K = Keep()
+    rc = lib.fm_matching_cost(K(XA), K(valid.astype(np.uint8)), K(mean),
+                              K(cov.reshape(nt, 64)), ptr(slots), K(tl), nt, K(XB),
+                              K(det_tlbr), K(dl), K(occ.astype(np.uint8)), K(sel),
                               len(sel), 512, 1 if metric == 'cosine' else 0, 0.9, 0.2, 0.8, kf.params, ptr(out),
                               stream_ptr())
     _lib.check(rc, "fm_matching_cost")
@@ -124,17 +125,18 @@ def test_matching_cost_fused(prim, lib, metric):
 
 def test_cdist_golden(prim, lib):
     """cdist alone (motion off, gate off) against the reference's own cdist output."""
-    from gpu_util import dev, host, kalman_params
+    from gpu_util import dev, host, kalman_params, Keep
     from fastmot_b200 import _lib
     from fastmot_b200.devmem import ptr, stream_ptr
     kf = kalman_params()
+    K = Keep()
     XA, XB, mask = prim['cd_XA'], prim['cd_XB'], prim['cd_mask']
     nt, nd = len(XA), len(XB)
     out = torch.zeros(nt, nd, dtype=torch.float64, device="cuda")
     z = torch.zeros(nt, 64, dtype=torch.float64, device="cuda")
     for metric, key in ((1, 'cd_cos'), (0, 'cd_euc')):
-        rc = lib.fm_matching_cost(ptr(dev(XA)), None, ptr(z), ptr(z), ptr(dev(np.arange(nt, dtype=np.int32))), None,
-                                  nt, ptr(dev(XB)), ptr(z), None, None, None, nd, 512, metric, 0.9, -1.0, -1.0,
+        rc = lib.fm_matching_cost(K(XA), None, ptr(z), ptr(z), K(np.arange(nt, dtype=np.int32)), None,
+                                  nt, K(XB), ptr(z), None, None, None, nd, 512, metric, 0.9, -1.0, -1.0,
                                   kf.params, ptr(out), stream_ptr())
         _lib.check(rc, "fm_matching_cost")
         got = host(out)
@@ -142,17 +144,18 @@ def test_cdist_golden(prim, lib):
 
 
 def test_iou_and_occlusion(prim, lib):
-    from gpu_util import dev, host
+    from gpu_util import dev, host, Keep
     from fastmot_b200 import _lib
     from fastmot_b200.devmem import ptr, stream_ptr
+    K = Keep()
     a, b = prim['iou_a'], prim['iou_b']
     out = torch.zeros(len(a), len(b), dtype=torch.float64, device="cuda")
-    _lib.check(lib.fm_iou_cost(ptr(dev(a)), None, None, len(a), ptr(dev(b)), None, None, len(b), -1.0, ptr(out),
+    _lib.check(lib.fm_iou_cost(K(a), None, None, len(a), K(b), None, None, len(b), -1.0, ptr(out),
                                stream_ptr()), "iou")
     np.testing.assert_allclose(host(out), prim['iou_dist'], atol=1e-12)
     boxes = prim['occ_in']
     occ = torch.zeros(len(boxes), dtype=torch.uint8, device="cuda")
-    _lib.check(lib.fm_find_occluded(ptr(dev(boxes)), len(boxes), float(prim['occ_thresh']), ptr(occ),
+    _lib.check(lib.fm_find_occluded(K(boxes), len(boxes), float(prim['occ_thresh']), ptr(occ),
                                     stream_ptr()), "occ")
     np.testing.assert_array_equal(host(occ).astype(bool), prim['occ_out'])
 
@@ -230,9 +233,10 @@ def test_greedy_golden(prim):
 
 
 def test_feature_update_matches_reference_semantics(lib):
-    from gpu_util import dev, host
+    from gpu_util import dev, host, Keep
     from fastmot_b200 import _lib
     from fastmot_b200.devmem import ptr, stream_ptr
+    K = Keep()
     rng = np.random.default_rng(2)
     E = 512
     vec = rng.normal(size=(6, E)).astype(np.float32)
@@ -254,9 +258,9 @@ def test_feature_update_matches_reference_semantics(lib):
             hs[slot] = hs[slot] + vec[vi]
             av = (hs[slot].astype(np.float64) * (1. / cnt[slot])).astype(np.float32)
             ha[slot] = (av.astype(np.float64) * (1. / np.linalg.norm(av))).astype(np.float32)
-        _lib.check(lib.fm_feature_update(ptr(s), ptr(a), ptr(last), ptr(v), ptr(dev(np.array([slot], np.int32))),
-                                         ptr(dev(vec)), ptr(dev(np.array([vi], np.int32))),
-                                         ptr(dev(np.array([cnt[slot]], np.int32))), 1, E, stream_ptr()), "feat")
+        _lib.check(lib.fm_feature_update(ptr(s), ptr(a), ptr(last), ptr(v), K(np.array([slot], np.int32)),
+                                         K(vec), K(np.array([vi], np.int32)),
+                                         K(np.array([cnt[slot]], np.int32)), 1, E, stream_ptr()), "feat")
     for slot in hs:
         np.testing.assert_allclose(host(s)[slot], hs[slot], atol=1e-6)
         np.testing.assert_allclose(host(a)[slot], ha[slot], atol=1e-6)
