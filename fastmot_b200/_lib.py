@@ -24,6 +24,15 @@ class FmKalmanParams(C.Structure):
                 ("init_pos_weight", c_d), ("init_vel_weight", c_d)]
 
 
+class FmPyramid(C.Structure):
+    _fields_ = [("n_levels", c_i), ("w", c_i * 8), ("h", c_i * 8), ("img", c_p * 8), ("deriv", c_p * 8)]
+
+
+class FmTrackJob(C.Structure):
+    _fields_ = [("slot", c_i), ("x0", c_i), ("y0", c_i), ("cw", c_i), ("ch", c_i), ("area", c_i), ("n_keep", c_i),
+                ("redetect", c_i), ("min_dist", c_i), ("scratch_off", c_i), ("eig_max", c_f), ("pad", c_i)]
+
+
 class FmYoloHead(C.Structure):
     _fields_ = [("anchors", c_f * 12), ("scale_x_y", c_f)]
 
@@ -51,6 +60,19 @@ SIGNATURES = {
     "fm_roi_resize_norm": (c_i, [c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
     "fm_yolo_decode_filter": (c_i, [c_p, c_i, c_i, c_i, c_i, C.POINTER(FmYoloHead), c_i, c_i, c_i, c_i, c_i, c_p,
                                      c_d, c_f, c_f, c_f, c_f, c_p, c_p, c_p, c_i, c_p]),
+    "fm_gray_half": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p]),
+    "fm_pyr_level": (c_i, [c_p, c_i, c_i, c_p, c_p]),
+    "fm_scharr": (c_i, [c_p, c_i, c_i, c_p, c_p]),
+    "fm_bg_small": (c_i, [c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_p]),
+    "fm_flow_keypoints": (c_i, [c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_i, c_d, c_d, c_d, c_i, c_p, c_p, c_i,
+                                 c_p, c_p, c_p]),
+    "fm_fast_detect": (c_i, [c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p, c_i, c_p]),
+    "fm_gather_points": (c_i, [c_p, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_p]),
+    "fm_lk_track": (c_i, [c_p, c_p, c_p, c_p, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_f, c_p, c_p, c_p, c_p]),
+    "fm_ransac_homography": (c_i, [c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i,
+                                    c_p]),
+    "fm_ransac_affine_partial_batch": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
+                                              c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_d, c_d, c_i, c_i, c_i, c_p]),
     "fm_nms_mask_bytes": (c_ll, [c_i]),
     "fm_diou_nms_filter": (c_i, [c_p, c_p, c_p, c_i, c_d, c_d, c_d, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
 }

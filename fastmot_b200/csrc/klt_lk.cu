@@ -1,0 +1,214 @@
+// Pyramidal Lucas-Kanade sparse optical flow, 8 lanes per point (one lane per window row, warp shuffles for the
+// window sums), all pyramid levels inside one launch.
+//
+// Restates cv2.calcOpticalFlowPyrLK as called at fastmot/flow.py:203-209 (winSize 5x5, maxLevel 5,
+// criteria (COUNT|EPS, 10, 0.03), flags 0, minEigThreshold 1e-4): OpenCV lkpyramid.cpp LKTrackerInvoker —
+// Q14 bilinear weights, int16 Scharr derivatives, patch values descaled to 5 fractional bits, window sums in
+// fp32, err = mean |I - J| over the window / 32.  Float summation order differs from OpenCV's SIMD lanes, so
+// results agree to ~1e-4 px rather than bitwise (SURVEY.md §8c tier T2).
+#include "common.cuh"
+#include "../../include/fastmot_b200.h"
+
+namespace {
+
+#define LK_W_BITS 14
+#define LK_MAX_WIN 8
+
+__device__ __forceinline__ int refl101(int p, int n) {
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = p < 0 ? -p : 2 * n - 2 - p;
+    return p;
+}
+
+__device__ __forceinline__ float group_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+}
+
+__device__ __forceinline__ int px(const unsigned char* img, int w, int h, int x, int y) {
+    return img[(size_t)refl101(y, h) * w + refl101(x, w)];
+}
+
+__device__ __forceinline__ short2 dv(const short2* d, int w, int h, int x, int y) {
+    if (x < 0 || y < 0 || x >= w || y >= h) return make_short2(0, 0);  // BORDER_CONSTANT 0 on derivatives
+    return d[(size_t)y * w + x];
+}
+
+__global__ void __launch_bounds__(128) lk_kernel(FmPyramid prev, FmPyramid cur, const float* __restrict__ pts_full,
+                                                  const int* __restrict__ meta, float pt_scale_x, float pt_scale_y,
+                                                  int win_w, int win_h, int max_count, float eps_sq, float min_eig_thr,
+                                                  float max_error, float unscale_x, float unscale_y,
+                                                  float* __restrict__ out_pts, unsigned char* __restrict__ out_status,
+                                                  float* __restrict__ out_err) {
+    const int n_pts = meta[1];
+    const int lane8 = threadIdx.x & 7;
+    const int groups_per_block = blockDim.x >> 3;
+    const int n_levels = prev.n_levels;
+    const float half_w = (win_w - 1) * 0.5f, half_h = (win_h - 1) * 0.5f;
+    const bool row_on = lane8 < win_h;
+    for (int base = blockIdx.x * groups_per_block; base < n_pts; base += gridDim.x * groups_per_block) {
+        const int p = base + (threadIdx.x >> 3);
+        const bool valid = p < n_pts;
+        // _scale_pts (flow.py:327-331): full-res -> optical-flow resolution, f32
+        const float ptx = valid ? pts_full[2 * p] * pt_scale_x : 0.f;
+        const float pty = valid ? pts_full[2 * p + 1] * pt_scale_y : 0.f;
+        float nx = 0.f, ny = 0.f;  // nextPts[ptidx]
+        bool status = valid;
+        float err = 0.f;
+        for (int level = n_levels - 1; level >= 0; --level) {
+            const int W = prev.w[level], H = prev.h[level];
+            const unsigned char* I = prev.img[level];
+            const unsigned char* J = cur.img[level];
+            const short2* dI = (const short2*)prev.deriv[level];
+            const float sc = (float)(1. / (1 << level));
+            float ppx = ptx * sc, ppy = pty * sc;
+            if (level == n_levels - 1) { nx = ppx; ny = ppy; } else { nx *= 2.f; ny *= 2.f; }
+            ppx -= half_w; ppy -= half_h;
+            int ix = (int)floorf(ppx), iy = (int)floorf(ppy);
+            bool lvl_on = valid;
+            if (ix < -win_w || ix >= W || iy < -win_h || iy >= H) {
+                if (level == 0) { status = false; err = 0.f; }
+                lvl_on = false;
+            }
+            float a = ppx - ix, b = ppy - iy;
+            int iw00 = (int)rintf((1.f - a) * (1.f - b) * (1 << LK_W_BITS));
+            int iw01 = (int)rintf(a * (1.f - b) * (1 << LK_W_BITS));
+            int iw10 = (int)rintf((1.f - a) * b * (1 << LK_W_BITS));
+            int iw11 = (1 << LK_W_BITS) - iw00 - iw01 - iw10;
+            short Iv[LK_MAX_WIN], Ix[LK_MAX_WIN], Iy[LK_MAX_WIN];
+            float A11 = 0.f, A12 = 0.f, A22 = 0.f;
+            if (lvl_on && row_on) {
+                const int y = iy + lane8;
+#pragma unroll
+                for (int x = 0; x < LK_MAX_WIN; ++x) {
+                    if (x >= win_w) break;
+                    const int xx = ix + x;
+                    const int ival = (px(I, W, H, xx, y) * iw00 + px(I, W, H, xx + 1, y) * iw01 +
+                                      px(I, W, H, xx, y + 1) * iw10 + px(I, W, H, xx + 1, y + 1) * iw11 +
+                                      (1 << (LK_W_BITS - 5 - 1))) >> (LK_W_BITS - 5);
+                    const short2 d00 = dv(dI, W, H, xx, y), d01 = dv(dI, W, H, xx + 1, y);
+                    const short2 d10 = dv(dI, W, H, xx, y + 1), d11 = dv(dI, W, H, xx + 1, y + 1);
+                    const int ixv = (d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11 +
+                                     (1 << (LK_W_BITS - 1))) >> LK_W_BITS;
+                    const int iyv = (d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11 +
+                                     (1 << (LK_W_BITS - 1))) >> LK_W_BITS;
+                    Iv[x] = (short)ival; Ix[x] = (short)ixv; Iy[x] = (short)iyv;
+                    A11 += (float)(ixv * ixv); A12 += (float)(ixv * iyv); A22 += (float)(iyv * iyv);
+                }
+            }
+            A11 = group_sum(A11); A12 = group_sum(A12); A22 = group_sum(A22);
+            const float FLT_SCALE = 1.f / (1 << 20);
+            A11 *= FLT_SCALE; A12 *= FLT_SCALE; A22 *= FLT_SCALE;
+            float D = A11 * A22 - A12 * A12;
+            const float min_eig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) /
+                                  (2 * win_w * win_h);
+            if (lvl_on && (min_eig < min_eig_thr || D < 1.1920929e-07f)) {
+                if (level == 0) status = false;
+                lvl_on = false;
+            }
+            D = 1.f / D;
+            float cx = nx - half_w, cy = ny - half_h;  // nextPt -= halfWin
+            float pdx = 0.f, pdy = 0.f;
+            bool iter_on = lvl_on;
+            for (int j = 0; j < max_count; ++j) {
+                if (!__any_sync(0xffffffffu, iter_on)) break;
+                const int jx = (int)floorf(cx), jy = (int)floorf(cy);
+                if (iter_on && (jx < -win_w || jx >= W || jy < -win_h || jy >= H)) {
+                    if (level == 0) status = false;
+                    iter_on = false;
+                }
+                const float a2 = cx - jx, b2 = cy - jy;
+                const int jw00 = (int)rintf((1.f - a2) * (1.f - b2) * (1 << LK_W_BITS));
+                const int jw01 = (int)rintf(a2 * (1.f - b2) * (1 << LK_W_BITS));
+                const int jw10 = (int)rintf((1.f - a2) * b2 * (1 << LK_W_BITS));
+                const int jw11 = (1 << LK_W_BITS) - jw00 - jw01 - jw10;
+                float b1 = 0.f, b2s = 0.f;
+                if (iter_on && row_on) {
+                    const int y = jy + lane8;
+#pragma unroll
+                    for (int x = 0; x < LK_MAX_WIN; ++x) {
+                        if (x >= win_w) break;
+                        const int xx = jx + x;
+                        const int jval = (px(J, W, H, xx, y) * jw00 + px(J, W, H, xx + 1, y) * jw01 +
+                                          px(J, W, H, xx, y + 1) * jw10 + px(J, W, H, xx + 1, y + 1) * jw11 +
+                                          (1 << (LK_W_BITS - 5 - 1))) >> (LK_W_BITS - 5);
+                        const int diff = jval - Iv[x];
+                        b1 += (float)(diff * Ix[x]);
+                        b2s += (float)(diff * Iy[x]);
+                    }
+                }
+                b1 = group_sum(b1) * FLT_SCALE;
+                b2s = group_sum(b2s) * FLT_SCALE;
+                if (iter_on) {
+                    const float dx = (A12 * b2s - A22 * b1) * D, dy = (A12 * b1 - A11 * b2s) * D;
+                    cx += dx; cy += dy;
+                    nx = cx + half_w; ny = cy + half_h;
+                    if (dx * dx + dy * dy <= eps_sq) {
+                        iter_on = false;
+                    } else if (j > 0 && fabsf(dx + pdx) < 0.01f && fabsf(dy + pdy) < 0.01f) {
+                        nx -= dx * 0.5f; ny -= dy * 0.5f;
+                        iter_on = false;
+                    }
+                    pdx = dx; pdy = dy;
+                }
+            }
+            if (level == 0) {
+                // err = mean |J - I| over the window / 32 at the final position
+                const float ex = nx - half_w, ey = ny - half_h;
+                const int jx = (int)floorf(ex), jy = (int)floorf(ey);
+                bool err_on = status;
+                if (err_on && (jx < -win_w || jx >= W || jy < -win_h || jy >= H)) { status = false; err_on = false; }
+                const float a2 = ex - jx, b2 = ey - jy;
+                const int jw00 = (int)rintf((1.f - a2) * (1.f - b2) * (1 << LK_W_BITS));
+                const int jw01 = (int)rintf(a2 * (1.f - b2) * (1 << LK_W_BITS));
+                const int jw10 = (int)rintf((1.f - a2) * b2 * (1 << LK_W_BITS));
+                const int jw11 = (1 << LK_W_BITS) - jw00 - jw01 - jw10;
+                float ev = 0.f;
+                if (err_on && row_on) {
+                    const int y = jy + lane8;
+#pragma unroll
+                    for (int x = 0; x < LK_MAX_WIN; ++x) {
+                        if (x >= win_w) break;
+                        const int xx = jx + x;
+                        const int jval = (px(J, W, H, xx, y) * jw00 + px(J, W, H, xx + 1, y) * jw01 +
+                                          px(J, W, H, xx, y + 1) * jw10 + px(J, W, H, xx + 1, y + 1) * jw11 +
+                                          (1 << (LK_W_BITS - 5 - 1))) >> (LK_W_BITS - 5);
+                        ev += (float)abs(jval - Iv[x]);
+                    }
+                }
+                ev = group_sum(ev);
+                if (err_on) err = ev * (1.f / (32 * win_w * win_h));
+            }
+        }
+        if (valid && lane8 == 0) {
+            // _get_status (flow.py:348-349) and _unscale_pts with mask (flow.py:335-344)
+            const bool good = status && (err < max_error);
+            out_status[p] = good ? 1 : 0;
+            out_err[p] = err;
+            out_pts[2 * p] = good ? nx * unscale_x : nx;
+            out_pts[2 * p + 1] = good ? ny * unscale_y : ny;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int fm_lk_track(const FmPyramid* prev, const FmPyramid* cur, const float* pts_full, const int* meta,
+                           float pt_scale_x, float pt_scale_y, int win_w, int win_h, int max_count, float epsilon,
+                           float min_eig_thr, float max_error, float* out_pts, unsigned char* out_status,
+                           float* out_err, void* stream) {
+    FM_REQUIRE(prev && cur, "fm_lk_track: pyramids are NULL");
+    FM_REQUIRE(win_w >= 1 && win_w <= LK_MAX_WIN && win_h >= 1 && win_h <= LK_MAX_WIN, "fm_lk_track: window > 8");
+    FM_REQUIRE(prev->n_levels == cur->n_levels && prev->n_levels <= FM_MAX_PYR_LEVELS, "fm_lk_track: levels");
+    // OpenCV clamps the criteria: maxCount in [0,100], epsilon in [0,10], then squares epsilon
+    max_count = max_count < 0 ? 0 : (max_count > 100 ? 100 : max_count);
+    double e = epsilon < 0 ? 0 : (epsilon > 10 ? 10 : epsilon);
+    lk_kernel<<<FM_NUM_SMS * 8, 128, 0, (cudaStream_t)stream>>>(*prev, *cur, pts_full, meta, pt_scale_x, pt_scale_y,
+                                                                win_w, win_h, max_count, (float)(e * e), min_eig_thr,
+                                                                max_error, 1.0f / pt_scale_x, 1.0f / pt_scale_y,
+                                                                out_pts, out_status, out_err);
+    FM_CHECK_LAUNCH("fm_lk_track");
+    return FM_OK;
+}

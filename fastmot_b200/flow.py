@@ -1,24 +1,264 @@
-"""KLT flow front-end (API of fastmot/flow.py:16-264).  Placeholder until csrc/klt_*.cu lands."""
+"""KLT optical-flow stage on the GPU with the reference's constructor / attributes (fastmot/flow.py:16-264).
+
+`predict_device` enqueues the whole of `Flow.predict` — gray + 0.5x pyramid with Scharr derivatives, occlusion
+("owner") map, per-track keypoint filtering and Shi-Tomasi re-detection, FAST background corners, pyramidal LK on
+all points at once, RANSAC homography, per-track RANSAC partial-affine with box prediction — as ~15 kernel
+launches with no OpenCV and no host round trip except one 16-byte status read.  Results stay on the device:
+predicted boxes / flags / inlier ratios in the track pool, the homography in a 9-double buffer that the batched
+Kalman kernel reads directly.
+"""
+import ctypes as C
+import logging
+
 import numpy as np
+import torch
+
+from . import _lib
+from .devmem import ptr, stream_ptr, FrameUploader
+
+LOGGER = logging.getLogger(__name__)
 
 
 class Flow:
-    def __init__(self, size, bg_feat_scale_factor=(0.1, 0.1), opt_flow_scale_factor=(0.5, 0.5), feat_density=0.005,
-                 feat_dist_factor=0.06, ransac_max_iter=500, ransac_conf=0.99, max_error=100, inlier_thresh=4,
-                 bg_feat_thresh=10, obj_feat_params=None, opt_flow_params=None):
+    def __init__(self, size,
+                 bg_feat_scale_factor=(0.1, 0.1),
+                 opt_flow_scale_factor=(0.5, 0.5),
+                 feat_density=0.005,
+                 feat_dist_factor=0.06,
+                 ransac_max_iter=500,
+                 ransac_conf=0.99,
+                 max_error=100,
+                 inlier_thresh=4,
+                 bg_feat_thresh=10,
+                 obj_feat_params=None,
+                 opt_flow_params=None,
+                 max_points=1 << 18,
+                 max_bg_points=1 << 16,
+                 max_tracks=2048,
+                 scratch_floats=1 << 24):
         self.size = size
-        self.bg_keypoints = np.empty((0, 2), np.float32)
-        self.prev_bg_keypoints = np.empty((0, 2), np.float32)
+        assert 0 < bg_feat_scale_factor[0] <= 1 and 0 < bg_feat_scale_factor[1] <= 1
+        self.bg_feat_scale_factor = bg_feat_scale_factor
+        assert 0 < opt_flow_scale_factor[0] <= 1 and 0 < opt_flow_scale_factor[1] <= 1
+        self.opt_flow_scale_factor = opt_flow_scale_factor
+        assert 0 <= feat_density <= 1
+        self.feat_density = feat_density
+        assert feat_dist_factor >= 0
+        self.feat_dist_factor = feat_dist_factor
+        assert ransac_max_iter >= 0
+        self.ransac_max_iter = ransac_max_iter
+        assert 0 <= ransac_conf <= 1
+        self.ransac_conf = ransac_conf
+        assert 0 <= max_error <= 255
+        self.max_error = max_error
+        assert inlier_thresh >= 1
+        self.inlier_thresh = inlier_thresh
+        assert bg_feat_thresh >= 0
+        self.bg_feat_thresh = bg_feat_thresh
+
+        self.obj_feat_params = {"maxCorners": 1000, "qualityLevel": 0.06, "blockSize": 3}
+        # the reference ignores the configured opt_flow_params (inverted `is None`, flow.py:92-93) and always
+        # runs with these values; accept the argument, keep the reference's effective behaviour
+        self.opt_flow_params = {"winSize": (5, 5), "maxLevel": 5, "criteria": (3, 10, 0.03)}
+        if obj_feat_params is not None:
+            self.obj_feat_params.update(vars(obj_feat_params))
+        if self.obj_feat_params["blockSize"] != 3:
+            raise NotImplementedError("Shi-Tomasi kernel is written for blockSize 3 (the reference default)")
+        if tuple(opt_flow_scale_factor) != (0.5, 0.5) or size[0] % 2 or size[1] % 2:
+            raise NotImplementedError("optical-flow scale must be 0.5 on an even frame size (2x2 mean kernel)")
+
+        self._lib = _lib.require_device()
+        W, H = size
+        dev = torch.device("cuda")
+        u8, i32, f32 = torch.uint8, torch.int32, torch.float32
+        self.opt_flow_sz = (round(opt_flow_scale_factor[0] * W), round(opt_flow_scale_factor[1] * H))
+        self.bg_feat_sz = (round(bg_feat_scale_factor[0] * W), round(bg_feat_scale_factor[1] * H))
+        win_w, win_h = self.opt_flow_params["winSize"]
+        # pyramid geometry of cv::buildOpticalFlowPyramid
+        sizes = [self.opt_flow_sz]
+        for _ in range(self.opt_flow_params["maxLevel"]):
+            w, h = (sizes[-1][0] + 1) // 2, (sizes[-1][1] + 1) // 2
+            if w <= win_w or h <= win_h:
+                break
+            sizes.append((w, h))
+        self.level_sizes = sizes
+        self.gray = [torch.zeros(H, W, dtype=u8, device=dev) for _ in range(2)]
+        self.pyr = [[torch.zeros(h, w, dtype=u8, device=dev) for (w, h) in sizes] for _ in range(2)]
+        self.deriv = [[torch.zeros(h, w, 2, dtype=torch.int16, device=dev) for (w, h) in sizes] for _ in range(2)]
+        self.pyr_desc = []
+        for k in range(2):
+            d = _lib.FmPyramid()
+            d.n_levels = len(sizes)
+            for i, (w, h) in enumerate(sizes):
+                d.w[i], d.h[i] = w, h
+                d.img[i] = self.pyr[k][i].data_ptr()
+                d.deriv[i] = self.deriv[k][i].data_ptr()
+            self.pyr_desc.append(d)
+        self.prev = 0
+        self.owner = torch.zeros(H, W, dtype=i32, device=dev)
+        bw, bh = self.bg_feat_sz
+        self.bg = torch.zeros(bh, bw, dtype=u8, device=dev)
+        self.bg_mask = torch.zeros(bh, bw, dtype=u8, device=dev)
+        self.bg_score = torch.zeros(bh, bw, dtype=u8, device=dev)
+        self.max_points, self.max_bg, self.max_tracks = max_points, max_bg_points, max_tracks
+        self.bg_pts = torch.zeros(max_bg_points, 2, dtype=f32, device=dev)
+        self.bg_count = torch.zeros(1, dtype=i32, device=dev)
+        self.all_prev = torch.zeros(max_points, 2, dtype=f32, device=dev)
+        self.all_cur = torch.zeros(max_points, 2, dtype=f32, device=dev)
+        self.status = torch.zeros(max_points, dtype=u8, device=dev)
+        self.err = torch.zeros(max_points, dtype=f32, device=dev)
+        self.trk_begin = torch.zeros(max_tracks + 1, dtype=i32, device=dev)
+        self.slots_dev = torch.zeros(max_tracks, dtype=i32, device=dev)
+        self.meta = torch.zeros(4, dtype=i32, device=dev)
+        self.jobs = torch.zeros(max_tracks * C.sizeof(_lib.FmTrackJob), dtype=u8, device=dev)
+        self.scratch = torch.zeros(scratch_floats, dtype=f32, device=dev)
+        self.scratch_cap = scratch_floats
+        self.flags = torch.zeros(32, dtype=i32, device=dev)   # [0] scratch counter, [1] kp status, [8:24] round flags
+        self.good_idx = torch.zeros(max_bg_points, dtype=i32, device=dev)
+        self.inl_idx = torch.zeros(max_bg_points, dtype=i32, device=dev)
+        self.bg_kp = torch.zeros(max_bg_points, 2, dtype=f32, device=dev)
+        self.bg_kp_prev = torch.zeros(max_bg_points, 2, dtype=f32, device=dev)
+        self.bg_kp_count = torch.zeros(1, dtype=i32, device=dev)
+        self.est_boxes = torch.zeros(2 * max_tracks * 5, dtype=i32, device=dev)
+        self.sig = torch.zeros(max_tracks, dtype=torch.int64, device=dev)
+        self._h_flags = torch.zeros(32, dtype=i32).pin_memory()
+        self._h_slots = torch.zeros(max_tracks, dtype=i32).pin_memory()
+        self._uploader = FrameUploader(size)
         self.pool = None
+        self._order = []
+        self._bg_cache = None
+        self.rounds_last = 0
 
     def bind_pool(self, pool):
         self.pool = pool
 
+    # ------------------------------------------------------------------ lazily fetched attributes
+    def _fetch_bg(self):
+        if self._bg_cache is None:
+            n = int(self.bg_kp_count.item())
+            self._bg_cache = (self.bg_kp_prev[:n].cpu().numpy().copy(), self.bg_kp[:n].cpu().numpy().copy())
+        return self._bg_cache
+
+    @property
+    def bg_keypoints(self):
+        return self._fetch_bg()[1]
+
+    @property
+    def prev_bg_keypoints(self):
+        return self._fetch_bg()[0]
+
+    # ------------------------------------------------------------------
+    def _to_device(self, frame):
+        return frame if torch.is_tensor(frame) else self._uploader.upload(frame)
+
+    def _preprocess(self, frame_dev, k):
+        """cvtColor + 0.5x resize (flow.py:153-154) and the LK pyramid with derivatives for buffer k."""
+        W, H = self.size
+        s = stream_ptr()
+        lib = self._lib
+        _lib.check(lib.fm_gray_half(ptr(frame_dev), W, H, ptr(self.gray[k]), ptr(self.pyr[k][0]), s), "fm_gray_half")
+        for i, (w, h) in enumerate(self.level_sizes):
+            if i + 1 < len(self.level_sizes):
+                _lib.check(lib.fm_pyr_level(ptr(self.pyr[k][i]), w, h, ptr(self.pyr[k][i + 1]), s), "fm_pyr_level")
+            _lib.check(lib.fm_scharr(ptr(self.pyr[k][i]), w, h, ptr(self.deriv[k][i]), s), "fm_scharr")
+
     def init(self, frame):
-        pass
+        """flow.py:121-133"""
+        if frame is None:
+            return
+        self._preprocess(self._to_device(frame), self.prev)
+        self.bg_kp_count.zero_()
+        self._bg_cache = None
 
     def predict_device(self, frame, tracks, h_dev, h_ok_dev):
-        raise NotImplementedError("KLT kernels not built yet")
+        """Enqueue flow.py:135-264 for `tracks` (active Track objects); returns the nearest-first order
+        [(trk_id, slot)].  Homography -> h_dev (9 f64), success flag -> h_ok_dev (i32)."""
+        lib, pool = self._lib, self.pool
+        W, H = self.size
+        s = stream_ptr()
+        cur = 1 - self.prev
+        frame_dev = self._to_device(frame)
+        self._preprocess(frame_dev, cur)
+        # order tracks from closest to farthest (flow.py:157; Python's stable sort on Track.__lt__)
+        tracks.sort(reverse=True)
+        n = len(tracks)
+        if n > self.max_tracks:
+            raise MemoryError("more active tracks than Flow.max_tracks")
+        self._order = [(t.trk_id, t.slot) for t in tracks]
+        if n:
+            self._h_slots[:n] = torch.as_tensor(np.fromiter((t.slot for t in tracks), np.int32, n))
+            self.slots_dev[:n].copy_(self._h_slots[:n], non_blocking=True)
+        pool.klt_ok.zero_()
+        fl = self.flags.data_ptr()
+        mk = self.obj_feat_params
+        _lib.check(lib.fm_flow_keypoints(ptr(self.gray[self.prev]), W, H, ptr(pool.tlbr), ptr(self.slots_dev), n,
+                                         ptr(self.owner), ptr(pool.kp), ptr(pool.kp_count), pool.max_kp,
+                                         float(self.feat_density), float(self.feat_dist_factor),
+                                         float(mk["qualityLevel"]), int(mk["maxCorners"]), ptr(self.jobs),
+                                         ptr(self.scratch), self.scratch_cap, C.c_void_p(fl), C.c_void_p(fl + 4), s),
+                   "fm_flow_keypoints")
+        bw, bh = self.bg_feat_sz
+        _lib.check(lib.fm_bg_small(ptr(self.gray[self.prev]), ptr(self.owner), W, H, ptr(self.bg), ptr(self.bg_mask),
+                                   bw, bh, s), "fm_bg_small")
+        ux = float(np.float32(1) / np.float32(self.bg_feat_scale_factor[0]))
+        uy = float(np.float32(1) / np.float32(self.bg_feat_scale_factor[1]))
+        _lib.check(lib.fm_fast_detect(ptr(self.bg), ptr(self.bg_mask), bw, bh, int(self.bg_feat_thresh), ux, uy,
+                                      ptr(self.bg_score), ptr(self.bg_pts), ptr(self.bg_count), self.max_bg, s),
+                   "fm_fast_detect")
+        _lib.check(lib.fm_gather_points(ptr(pool.kp), ptr(pool.kp_count), pool.max_kp, ptr(self.slots_dev), n,
+                                        ptr(self.bg_pts), ptr(self.bg_count), ptr(self.all_prev),
+                                        ptr(self.trk_begin), ptr(self.meta), self.max_points, s), "fm_gather_points")
+        win = self.opt_flow_params["winSize"]
+        crit = self.opt_flow_params["criteria"]
+        _lib.check(lib.fm_lk_track(C.byref(self.pyr_desc[self.prev]), C.byref(self.pyr_desc[cur]), ptr(self.all_prev),
+                                   ptr(self.meta), float(self.opt_flow_scale_factor[0]),
+                                   float(self.opt_flow_scale_factor[1]), int(win[0]), int(win[1]), int(crit[1]),
+                                   float(crit[2]), 1e-4, float(self.max_error), ptr(self.all_cur), ptr(self.status),
+                                   ptr(self.err), s), "fm_lk_track")
+        self.prev = cur   # flow.py:212-213
+        _lib.check(lib.fm_ransac_homography(ptr(self.all_prev), ptr(self.all_cur), ptr(self.status), ptr(self.meta),
+                                            int(self.ransac_max_iter), float(self.ransac_conf), 3.0,
+                                            int(self.inlier_thresh), ptr(self.good_idx), ptr(self.inl_idx),
+                                            ptr(h_dev), ptr(h_ok_dev), ptr(self.bg_kp), ptr(self.bg_kp_prev),
+                                            ptr(self.bg_kp_count), self.max_bg, s), "fm_ransac_homography")
+        self._bg_cache = None
+        rounds = 0
+        while True:
+            step = 2
+            _lib.check(lib.fm_ransac_affine_partial_batch(
+                ptr(self.all_prev), ptr(self.all_cur), ptr(self.status), ptr(self.trk_begin), ptr(self.slots_dev), n,
+                step, C.c_void_p(fl + 32), ptr(h_ok_dev), ptr(self.est_boxes), ptr(self.sig), ptr(pool.tlbr),
+                ptr(pool.klt_tlbr), ptr(pool.klt_ok), ptr(pool.inlier_ratio), ptr(pool.kp), ptr(pool.kp_prev),
+                ptr(pool.kp_count), pool.max_kp, W, H, int(self.ransac_max_iter), float(self.ransac_conf), 3.0,
+                int(self.inlier_thresh), 10, rounds, s), "fm_ransac_affine_partial_batch")
+            rounds += step
+            lib.fm_memcpy_async(C.c_void_p(self._h_flags.data_ptr()), C.c_void_p(fl), 128, s)
+            torch.cuda.current_stream().synchronize()
+            hf = self._h_flags.numpy()
+            if hf[1] != 0:
+                raise MemoryError(f"Flow scratch/candidate overflow (code {int(hf[1])}); raise scratch_floats")
+            if n == 0 or hf[8 + ((rounds - 1) & 15)] == 0 or rounds >= 2 * max(n, 1) + 2:
+                break
+        self.rounds_last = rounds
+        return self._order
 
-    def fetch_klt_bboxes(self, order):
-        return {}
+    def fetch_klt_bboxes(self, order=None):
+        """dict trk_id -> tlbr (f64) of the tracks whose box was predicted by the last predict_device."""
+        order = self._order if order is None else order
+        if not order:
+            return {}
+        slots = torch.as_tensor([s for _, s in order], device=self.pool.klt_ok.device)
+        ok = self.pool.klt_ok[slots].cpu().numpy()
+        boxes = self.pool.klt_tlbr[slots].cpu().numpy()
+        return {tid: boxes[i].copy() for i, (tid, _) in enumerate(order) if ok[i]}
+
+    def predict(self, frame, tracks):
+        """Drop-in `Flow.predict` (flow.py:135-264): returns (dict trk_id -> tlbr, 3x3 homography or None)."""
+        dev = self.pool.klt_ok.device
+        h = torch.zeros(9, dtype=torch.float64, device=dev)
+        ok = torch.zeros(1, dtype=torch.int32, device=dev)
+        order = self.predict_device(frame, tracks, h, ok)
+        if int(ok.item()) == 0:
+            LOGGER.warning('Camera motion estimation failed')
+            return {}, None
+        return self.fetch_klt_bboxes(order), h.cpu().numpy().reshape(3, 3)

@@ -163,6 +163,81 @@ int fm_diou_nms_filter(unsigned long long* keys, const float* dense, const int* 
                        int max_out, double* out_tlbr, long long* out_label, double* out_conf, int* out_count,
                        int* status, void* stream);
 
+/* ---------------------------------------------------------------- KLT optical flow (fastmot/flow.py) ---------- */
+#define FM_NO_OWNER 0x7fffffff
+#define FM_MAX_PYR_LEVELS 8
+
+typedef struct FmPyramid {       /* one image pyramid: u8 levels + int16x2 Scharr derivatives per level */
+    int n_levels;
+    int w[FM_MAX_PYR_LEVELS], h[FM_MAX_PYR_LEVELS];
+    const unsigned char* img[FM_MAX_PYR_LEVELS];
+    const short* deriv[FM_MAX_PYR_LEVELS];
+} FmPyramid;
+
+typedef struct FmTrackJob {      /* per-track record produced by fm_flow_keypoints (device) */
+    int slot, x0, y0, cw, ch, area, n_keep, redetect, min_dist, scratch_off;
+    float eig_max;
+    int pad;
+} FmTrackJob;
+
+/* cv2.cvtColor(BGR2GRAY) + cv2.resize(0.5x) of flow.py:153-154 / :129-131 in one pass (w, h even). */
+int fm_gray_half(const unsigned char* frame, int w, int h, unsigned char* gray, unsigned char* small, void* stream);
+/* one pyrDown step ((sw+1)/2 x (sh+1)/2) and the Scharr derivative image of a level — what
+ * cv2.calcOpticalFlowPyrLK builds internally (flow.py:203-207). */
+int fm_pyr_level(const unsigned char* src, int sw, int sh, unsigned char* dst, void* stream);
+int fm_scharr(const unsigned char* src, int w, int h, short* deriv, void* stream);
+/* flow.py:187-189: background-scale image (cv2.resize INTER_LINEAR) and nearest-neighbour mask from the owner map. */
+int fm_bg_small(const unsigned char* gray, const int* owner, int w, int h, unsigned char* bg, unsigned char* bg_mask,
+                int bw, int bh, void* stream);
+
+/* flow.py:156-184 for all active tracks (slots[] in nearest-first order, boxes from tlbr_pool): occlusion/owner
+ * map, keypoint filtering (_rect_filter), Shi-Tomasi re-detection (cv2.goodFeaturesToTrack, blockSize 3) where
+ * len(kp) < feat_density * area, ellipse filter.  Keypoints live in kp_pool[cap][max_kp][2] / kp_count[cap].
+ * scratch: scratch_cap floats for the eigenvalue maps; status[0] != 0 reports scratch/candidate overflow. */
+int fm_flow_keypoints(const unsigned char* prev_gray, int w, int h, const double* tlbr_pool, const int* slots,
+                      int n_trk, int* owner, float* kp_pool, int* kp_count, int max_kp, double feat_density,
+                      double feat_dist_factor, double quality, int max_corners, FmTrackJob* jobs, float* scratch,
+                      int scratch_cap, int* scratch_counter, int* status, void* stream);
+
+/* cv2.FastFeatureDetector(threshold, nonmaxSuppression=True, TYPE_9_16).detect(img, mask) (flow.py:190) followed
+ * by _unscale_pts (flow.py:335-344); output points in row-major order. score: w*h scratch bytes. */
+int fm_fast_detect(const unsigned char* img, const unsigned char* mask, int w, int h, int threshold, float unscale_x,
+                   float unscale_y, unsigned char* score, float* out_pts, int* out_count, int max_pts, void* stream);
+
+/* flow.py:182-186, 199-200: all_prev_pts = concat(track keypoints) ++ background points.
+ * trk_begin[n_trk + 1]; meta[0] = bg_begin, meta[1] = total points, meta[2] = #bg, meta[3] = overflow flag. */
+int fm_gather_points(const float* kp_pool, const int* kp_count, int max_kp, const int* slots, int n_trk,
+                     const float* bg_pts, const int* bg_count, float* all_pts, int* trk_begin, int* meta,
+                     int max_pts, void* stream);
+
+/* cv2.calcOpticalFlowPyrLK (flow.py:203-209) incl. _scale_pts / _get_status / _unscale_pts: points are given and
+ * returned in full-resolution coordinates; out_status = status & (err < max_error). n = meta[1]. */
+int fm_lk_track(const FmPyramid* h_prev, const FmPyramid* h_cur, const float* pts_full, const int* meta,
+                float pt_scale_x, float pt_scale_y, int win_w, int win_h, int max_count, float epsilon,
+                float min_eig_thr, float max_error, float* out_pts, unsigned char* out_status, float* out_err,
+                void* stream);
+
+/* cv2.findHomography(RANSAC, 3.0, maxIters, confidence) on the background matches + the failure tests of
+ * flow.py:215-232.  H_out[9] f64 (H[8] = 1), h_ok[0] = 1 on success; inlier points go to bg_kp / bg_kp_prev. */
+int fm_ransac_homography(const float* all_prev, const float* all_cur, const unsigned char* status, const int* meta,
+                         int max_iters, double confidence, double thresh, int inlier_thresh, int* good_idx,
+                         int* inl_idx, double* H_out, int* h_ok, float* bg_kp, float* bg_kp_prev, int* bg_kp_count,
+                         int max_bg, void* stream);
+
+/* cv2.estimateAffinePartial2D(RANSAC, 3.0, maxIters, confidence, refineIters) per track + _estimate_bbox + the
+ * acceptance tests and mask painting of flow.py:234-264.  The serial "paint predicted box, filter the next
+ * track's points" dependency is resolved by rounds: round r filters with the boxes of round r-1 and recomputes
+ * only tracks whose filtered point set changed; round_flags[r & 15] = 1 if anything changed (fixed point when 0).
+ * est_boxes: 2*n_trk*5 ints, sig: n_trk u64.  Results: klt_tlbr / klt_ok / inlier_ratio (slot-indexed pools),
+ * kp_pool <- inlier matched points, kp_prev_pool <- inlier previous points. */
+int fm_ransac_affine_partial_batch(const float* all_prev, const float* all_cur, const unsigned char* status,
+                                   const int* trk_begin, const int* slots, int n_trk, int n_rounds, int* round_flags,
+                                   const int* h_ok, int* est_boxes, unsigned long long* sig, double* tlbr_pool,
+                                   double* klt_tlbr, unsigned char* klt_ok, double* inlier_ratio, float* kp_pool,
+                                   float* kp_prev_pool, int* kp_count, int max_kp, int frame_w, int frame_h,
+                                   int max_iters, double confidence, double thresh, int inlier_thresh,
+                                   int refine_iters, int first_round, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
