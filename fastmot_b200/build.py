@@ -12,6 +12,10 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
 
+# LK must round every fp32 product like OpenCV's scalar code does (no FMA contraction) to stay bit-identical
+PER_FILE_FLAGS = {"klt_lk.cu": ["-fmad=false"]}
+
+
 def _stale(src, obj, deps):
     if not os.path.exists(obj):
         return True
@@ -34,7 +38,8 @@ def build(verbose=False, force=False):
 
     def compile_one(job):
         src, obj = job
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        extra = PER_FILE_FLAGS.get(os.path.basename(src), [])
+        cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, r
 

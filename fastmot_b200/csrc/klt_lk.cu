@@ -4,8 +4,8 @@
 // Restates cv2.calcOpticalFlowPyrLK as called at fastmot/flow.py:203-209 (winSize 5x5, maxLevel 5,
 // criteria (COUNT|EPS, 10, 0.03), flags 0, minEigThreshold 1e-4): OpenCV lkpyramid.cpp LKTrackerInvoker —
 // Q14 bilinear weights, int16 Scharr derivatives, patch values descaled to 5 fractional bits, window sums in
-// fp32, err = mean |I - J| over the window / 32.  Float summation order differs from OpenCV's SIMD lanes, so
-// results agree to ~1e-4 px rather than bitwise (SURVEY.md §8c tier T2).
+// fp32 IN OPENCV'S ROW-MAJOR ORDER (group_seq_sum), err = mean |I - J| over the window / 32.  The pure-Python
+// restatement of the same formulas (oracle/lk_restate.py) is bit-identical to cv2 4.13 on this image.
 #include "common.cuh"
 #include "../../include/fastmot_b200.h"
 
@@ -27,6 +27,33 @@ __device__ __forceinline__ float group_sum(float v) {
     return v;
 }
 
+// Sum of the per-lane row arrays in OpenCV's sequential row-major order (bit-exact fp32 accumulation):
+// lane r continues the running sum handed over by lane r-1.
+template <int NQ>
+__device__ __forceinline__ void group_seq_sum(float (*vals)[LK_MAX_WIN], int win_w, int win_h, int lane8, float* out) {
+    const int lane = threadIdx.x & 31, gbase = lane & ~7;
+    float acc[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) acc[q] = 0.f;
+    for (int r = 0; r < win_h; ++r) {
+        float in[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) in[q] = __shfl_sync(0xffffffffu, acc[q], gbase | (r > 0 ? r - 1 : 0));
+        if (lane8 == r) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                float a = r > 0 ? in[q] : 0.f;
+#pragma unroll
+                for (int x = 0; x < LK_MAX_WIN; ++x)
+                    if (x < win_w) a += vals[q][x];
+                acc[q] = a;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) out[q] = __shfl_sync(0xffffffffu, acc[q], gbase | (win_h - 1));
+}
+
 __device__ __forceinline__ int px(const unsigned char* img, int w, int h, int x, int y) {
     return img[(size_t)refl101(y, h) * w + refl101(x, w)];
 }
@@ -38,7 +65,7 @@ __device__ __forceinline__ short2 dv(const short2* d, int w, int h, int x, int y
 
 __global__ void __launch_bounds__(128) lk_kernel(FmPyramid prev, FmPyramid cur, const float* __restrict__ pts_full,
                                                   const int* __restrict__ meta, float pt_scale_x, float pt_scale_y,
-                                                  int win_w, int win_h, int max_count, float eps_sq, float min_eig_thr,
+                                                  int win_w, int win_h, int max_count, double eps_sq, float min_eig_thr,
                                                   float max_error, float unscale_x, float unscale_y,
                                                   float* __restrict__ out_pts, unsigned char* __restrict__ out_status,
                                                   float* __restrict__ out_err) {
@@ -78,7 +105,9 @@ __global__ void __launch_bounds__(128) lk_kernel(FmPyramid prev, FmPyramid cur, 
             int iw10 = (int)rintf((1.f - a) * b * (1 << LK_W_BITS));
             int iw11 = (1 << LK_W_BITS) - iw00 - iw01 - iw10;
             short Iv[LK_MAX_WIN], Ix[LK_MAX_WIN], Iy[LK_MAX_WIN];
-            float A11 = 0.f, A12 = 0.f, A22 = 0.f;
+            float pa[3][LK_MAX_WIN];
+#pragma unroll
+            for (int x = 0; x < LK_MAX_WIN; ++x) { pa[0][x] = 0.f; pa[1][x] = 0.f; pa[2][x] = 0.f; }
             if (lvl_on && row_on) {
                 const int y = iy + lane8;
 #pragma unroll
@@ -95,10 +124,12 @@ __global__ void __launch_bounds__(128) lk_kernel(FmPyramid prev, FmPyramid cur, 
                     const int iyv = (d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11 +
                                      (1 << (LK_W_BITS - 1))) >> LK_W_BITS;
                     Iv[x] = (short)ival; Ix[x] = (short)ixv; Iy[x] = (short)iyv;
-                    A11 += (float)(ixv * ixv); A12 += (float)(ixv * iyv); A22 += (float)(iyv * iyv);
+                    pa[0][x] = (float)(ixv * ixv); pa[1][x] = (float)(ixv * iyv); pa[2][x] = (float)(iyv * iyv);
                 }
             }
-            A11 = group_sum(A11); A12 = group_sum(A12); A22 = group_sum(A22);
+            float asum[3];
+            group_seq_sum<3>(pa, win_w, win_h, lane8, asum);
+            float A11 = asum[0], A12 = asum[1], A22 = asum[2];
             const float FLT_SCALE = 1.f / (1 << 20);
             A11 *= FLT_SCALE; A12 *= FLT_SCALE; A22 *= FLT_SCALE;
             float D = A11 * A22 - A12 * A12;
@@ -124,7 +155,9 @@ __global__ void __launch_bounds__(128) lk_kernel(FmPyramid prev, FmPyramid cur, 
                 const int jw01 = (int)rintf(a2 * (1.f - b2) * (1 << LK_W_BITS));
                 const int jw10 = (int)rintf((1.f - a2) * b2 * (1 << LK_W_BITS));
                 const int jw11 = (1 << LK_W_BITS) - jw00 - jw01 - jw10;
-                float b1 = 0.f, b2s = 0.f;
+                float pb[2][LK_MAX_WIN];
+#pragma unroll
+                for (int x = 0; x < LK_MAX_WIN; ++x) { pb[0][x] = 0.f; pb[1][x] = 0.f; }
                 if (iter_on && row_on) {
                     const int y = jy + lane8;
 #pragma unroll
@@ -135,17 +168,18 @@ __global__ void __launch_bounds__(128) lk_kernel(FmPyramid prev, FmPyramid cur, 
                                           px(J, W, H, xx, y + 1) * jw10 + px(J, W, H, xx + 1, y + 1) * jw11 +
                                           (1 << (LK_W_BITS - 5 - 1))) >> (LK_W_BITS - 5);
                         const int diff = jval - Iv[x];
-                        b1 += (float)(diff * Ix[x]);
-                        b2s += (float)(diff * Iy[x]);
+                        pb[0][x] = (float)(diff * Ix[x]);
+                        pb[1][x] = (float)(diff * Iy[x]);
                     }
                 }
-                b1 = group_sum(b1) * FLT_SCALE;
-                b2s = group_sum(b2s) * FLT_SCALE;
+                float bsum[2];
+                group_seq_sum<2>(pb, win_w, win_h, lane8, bsum);
+                const float b1 = bsum[0] * FLT_SCALE, b2s = bsum[1] * FLT_SCALE;
                 if (iter_on) {
                     const float dx = (A12 * b2s - A22 * b1) * D, dy = (A12 * b1 - A11 * b2s) * D;
                     cx += dx; cy += dy;
                     nx = cx + half_w; ny = cy + half_h;
-                    if (dx * dx + dy * dy <= eps_sq) {
+                    if ((double)dx * (double)dx + (double)dy * (double)dy <= eps_sq) {
                         iter_on = false;
                     } else if (j > 0 && fabsf(dx + pdx) < 0.01f && fabsf(dy + pdy) < 0.01f) {
                         nx -= dx * 0.5f; ny -= dy * 0.5f;
@@ -206,7 +240,7 @@ extern "C" int fm_lk_track(const FmPyramid* prev, const FmPyramid* cur, const fl
     max_count = max_count < 0 ? 0 : (max_count > 100 ? 100 : max_count);
     double e = epsilon < 0 ? 0 : (epsilon > 10 ? 10 : epsilon);
     lk_kernel<<<FM_NUM_SMS * 8, 128, 0, (cudaStream_t)stream>>>(*prev, *cur, pts_full, meta, pt_scale_x, pt_scale_y,
-                                                                win_w, win_h, max_count, (float)(e * e), min_eig_thr,
+                                                                win_w, win_h, max_count, e * e, min_eig_thr,
                                                                 max_error, 1.0f / pt_scale_x, 1.0f / pt_scale_y,
                                                                 out_pts, out_status, out_err);
     FM_CHECK_LAUNCH("fm_lk_track");
