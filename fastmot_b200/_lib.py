@@ -33,6 +33,12 @@ class FmTrackJob(C.Structure):
                 ("redetect", c_i), ("min_dist", c_i), ("scratch_off", c_i), ("eig_max", c_f), ("pad", c_i)]
 
 
+class FmConvDesc(C.Structure):
+    _fields_ = [(k, c_i) for k in ("n", "hi", "wi", "cin", "cin_stride", "cin_offset", "ho", "wo", "cout",
+                                   "cout_stride", "cout_offset", "kh", "kw", "stride", "pad", "act", "res_stride",
+                                   "res_offset")]
+
+
 class FmYoloHead(C.Structure):
     _fields_ = [("anchors", c_f * 12), ("scale_x_y", c_f)]
 
@@ -58,7 +64,7 @@ SIGNATURES = {
     "fm_greedy_match": (c_i, [c_p, c_i, c_i, c_d, c_p, c_p, c_p]),
     "fm_letterbox_preproc": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "fm_roi_resize_norm": (c_i, [c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
-    "fm_yolo_decode_filter": (c_i, [c_p, c_i, c_i, c_i, c_i, C.POINTER(FmYoloHead), c_i, c_i, c_i, c_i, c_i, c_p,
+    "fm_yolo_decode_filter": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, C.POINTER(FmYoloHead), c_i, c_i, c_i, c_i, c_i, c_p,
                                      c_d, c_f, c_f, c_f, c_f, c_p, c_p, c_p, c_i, c_p]),
     "fm_gray_half": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p]),
     "fm_pyr_level": (c_i, [c_p, c_i, c_i, c_p, c_p]),
@@ -73,6 +79,19 @@ SIGNATURES = {
                                     c_p]),
     "fm_ransac_affine_partial_batch": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
                                               c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_d, c_d, c_i, c_i, c_i, c_p]),
+    "fm_conv2d_simt": (c_i, [C.POINTER(FmConvDesc), c_p, c_p, c_p, c_p, c_p, c_p]),
+    "fm_maxpool": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "fm_maxpool_pad": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "fm_avgpool2": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
+    "fm_upsample_copy": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "fm_add_act": (c_i, [c_p, c_p, c_p, c_ll, c_i, c_p]),
+    "fm_add_act_strided": (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_p, c_i, c_i, c_ll, c_i, c_i, c_p]),
+    "fm_conv2d_tc": (c_i, [C.POINTER(FmConvDesc), c_p, c_p, c_p, c_p, c_p, c_p]),
+    "fm_conv2d_tc_supported": (c_i, [C.POINTER(FmConvDesc)]),
+    "fm_dwconv3": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "fm_global_avgpool": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p]),
+    "fm_channel_gate": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "fm_fc_norm": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "fm_nms_mask_bytes": (c_ll, [c_i]),
     "fm_diou_nms_filter": (c_i, [c_p, c_p, c_p, c_i, c_d, c_d, c_d, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
 }

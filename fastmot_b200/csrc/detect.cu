@@ -17,6 +17,7 @@ __device__ __forceinline__ float sigmoidf_fast(float x) { return 1.0f / (1.0f + 
 template <typename T>
 __global__ void yolo_decode_filter_kernel(const T* __restrict__ in, int yolo_w, int yolo_h, int num_anchors,
                                           FmYoloHead head, int num_classes, int input_w, int input_h, int new_coords,
+                                          int nhwc,
                                           int cand_base, const unsigned char* __restrict__ label_mask,
                                           double conf_thresh, float size_w, float size_h, float off_x, float off_y,
                                           float* __restrict__ dense, unsigned long long* __restrict__ keys,
@@ -26,15 +27,18 @@ __global__ void yolo_decode_filter_kernel(const T* __restrict__ in, int yolo_w, 
     if (idx >= total * num_anchors) return;
     const int info_len = 5 + num_classes;
     const int anchor = idx / total, cell = idx - anchor * total;
-    const T* cur = in + (size_t)anchor * info_len * total + cell;
+    // planar [(5+C)*A, H, W] (the TensorRT plugin's input) or channels-last [H, W, (5+C)*A] (our conv engine)
+    const size_t as = nhwc ? 1 : (size_t)total;
+    const T* cur = nhwc ? in + (size_t)cell * info_len * num_anchors + (size_t)anchor * info_len
+                        : in + (size_t)anchor * info_len * total + cell;
     int class_id = 0;
     float best = -INFINITY;
     for (int i = 5; i < info_len; ++i) {
-        float l = (float)cur[(size_t)i * total];
+        float l = (float)cur[(size_t)i * as];
         if (l > best) { best = l; class_id = i - 5; }
     }
-    const float t0 = (float)cur[0], t1 = (float)cur[(size_t)total], t2 = (float)cur[(size_t)2 * total],
-                t3 = (float)cur[(size_t)3 * total], t4 = (float)cur[(size_t)4 * total];
+    const float t0 = (float)cur[0], t1 = (float)cur[as], t2 = (float)cur[2 * as], t3 = (float)cur[3 * as],
+                t4 = (float)cur[4 * as];
     const int row = cell / yolo_w, col = cell - row * yolo_w;
     const float s = head.scale_x_y;
     float cls_prob, box_prob, bx, by, bw, bh;
@@ -216,7 +220,7 @@ __global__ void __launch_bounds__(32) nms_scan_kernel(const unsigned long long* 
 
 }  // namespace
 
-extern "C" int fm_yolo_decode_filter(const void* head_out, int is_fp16, int yolo_w, int yolo_h, int num_anchors,
+extern "C" int fm_yolo_decode_filter(const void* head_out, int is_fp16, int nhwc, int yolo_w, int yolo_h, int num_anchors,
                                      const FmYoloHead* head, int num_classes, int input_w, int input_h,
                                      int new_coords, int cand_base, const unsigned char* label_mask,
                                      double conf_thresh, float size_w, float size_h, float off_x, float off_y,
@@ -230,11 +234,11 @@ extern "C" int fm_yolo_decode_filter(const void* head_out, int is_fp16, int yolo
     if (is_fp16)
         yolo_decode_filter_kernel<__half><<<grid, 128, 0, (cudaStream_t)stream>>>(
             (const __half*)head_out, yolo_w, yolo_h, num_anchors, *head, num_classes, input_w, input_h, new_coords,
-            cand_base, label_mask, conf_thresh, size_w, size_h, off_x, off_y, dense, keys, counter, key_cap);
+            nhwc, cand_base, label_mask, conf_thresh, size_w, size_h, off_x, off_y, dense, keys, counter, key_cap);
     else
         yolo_decode_filter_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(
             (const float*)head_out, yolo_w, yolo_h, num_anchors, *head, num_classes, input_w, input_h, new_coords,
-            cand_base, label_mask, conf_thresh, size_w, size_h, off_x, off_y, dense, keys, counter, key_cap);
+            nhwc, cand_base, label_mask, conf_thresh, size_w, size_h, off_x, off_y, dense, keys, counter, key_cap);
     FM_CHECK_LAUNCH("fm_yolo_decode_filter");
     return FM_OK;
 }

@@ -152,7 +152,9 @@ class YOLODetector(Detector):
         lib = self._lib
         for hd, t in zip(self.heads, head_tensors):
             assert t.is_contiguous()
-            rc = lib.fm_yolo_decode_filter(ptr(t), 1 if t.dtype == torch.float16 else 0, hd['w'], hd['h'], hd['na'],
+            nhwc = 1 if getattr(self.backend, "heads_nhwc", False) else 0
+            rc = lib.fm_yolo_decode_filter(ptr(t), 1 if t.dtype == torch.float16 else 0, nhwc, hd['w'], hd['h'],
+                                           hd['na'],
                                            C.byref(hd['head']), self.model.NUM_CLASSES, self.input_wh[0],
                                            self.input_wh[1], 1 if self.model.NEW_COORDS else 0, hd['base'],
                                            ptr(self._label_mask_dev), float(self.conf_thresh),

@@ -1,0 +1,353 @@
+"""Conv-stack executors that take the place of the reference's TensorRT engines
+(fastmot/utils/inference.py:39-125): `YoloEngine` runs a Darknet layer list, `OSNetEngine` the OSNet op list,
+both on NHWC fp16 device tensors through the C-ABI layer kernels (csrc/nn.cu, csrc/conv_tc.cu).
+
+The launch sequence of a network is recorded once (static shapes) and replayed per call; with `use_graph=True`
+the replay is captured into a CUDA graph so a 170-layer detector costs one launch.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .devmem import ptr, stream_ptr
+from .models import darknet, osnet
+
+_ACT = darknet.ACTS
+
+
+class _Launch:
+    """A recorded C-ABI call: function + fully bound arguments."""
+    __slots__ = ("fn", "args", "what")
+
+    def __init__(self, fn, args, what):
+        self.fn, self.args, self.what = fn, args, what
+
+    def __call__(self, s):
+        rc = self.fn(*self.args, s)
+        if rc:
+            _lib.check(rc, self.what)
+
+
+def _conv_desc(n, hi, wi, cin, cin_stride, cin_off, ho, wo, cout, cout_stride, cout_off, k, stride, pad, act):
+    d = _lib.FmConvDesc()
+    d.n, d.hi, d.wi, d.cin, d.cin_stride, d.cin_offset = n, hi, wi, cin, cin_stride, cin_off
+    d.ho, d.wo, d.cout, d.cout_stride, d.cout_offset = ho, wo, cout, cout_stride, cout_off
+    d.kh = d.kw = k
+    d.stride, d.pad, d.act = stride, pad, act
+    d.res_stride = d.res_offset = 0
+    return d
+
+
+class _Net:
+    """Shared plumbing: recorded launches, optional CUDA-graph replay, conv dispatch (tcgen05 when supported)."""
+
+    def __init__(self, use_tc=True, use_graph=False):
+        self._lib = _lib.require_device()
+        self.use_tc = use_tc
+        self.use_graph = use_graph
+        self.launches = []
+        self._graph = None
+        self._keep = []
+        self.n_tc = self.n_simt = 0
+        self.dev = torch.device("cuda")
+
+    def _conv(self, desc, x, w, b, out, residual=None):
+        lib = self._lib
+        self._keep.append(desc)
+        if self.use_tc and lib.fm_conv2d_tc_supported(C.byref(desc)):
+            fn = lib.fm_conv2d_tc
+            self.n_tc += 1
+        else:
+            fn = lib.fm_conv2d_simt
+            self.n_simt += 1
+        self.launches.append(_Launch(fn, (C.byref(desc), ptr(x), ptr(w), ptr(b), ptr(residual), ptr(out)), "conv"))
+
+    def _add(self, fn_name, *args):
+        self.launches.append(_Launch(getattr(self._lib, fn_name), args, fn_name))
+
+    def replay(self):
+        if self.use_graph:
+            if self._graph is None:
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    sp = stream_ptr()
+                    for l in self.launches:      # warm-up outside capture
+                        l(sp)
+                torch.cuda.current_stream().wait_stream(s)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    sp = stream_ptr()
+                    for l in self.launches:
+                        l(sp)
+                self._graph = g
+            self._graph.replay()
+        else:
+            sp = stream_ptr()
+            for l in self.launches:
+                l(sp)
+
+
+class YoloEngine(_Net):
+    """Darknet graph executor.  forward(inp NHWC4 fp16) -> list of head tensors [H, W, (5+C)*A] fp16."""
+    heads_nhwc = True
+
+    def __init__(self, layers, input_hw, weights, use_tc=True, use_graph=False):
+        super().__init__(use_tc, use_graph)
+        H, W = input_hw
+        self.layers, self.shapes = darknet.infer_shapes(layers, 3, H, W)
+        self.inp = torch.zeros(H, W, 4, dtype=torch.float16, device=self.dev)
+        self.flops = darknet.count_flops(layers, 3, H, W)
+        L = self.layers
+        n = len(L)
+        # ---- plan: which layers are written straight into a concat buffer ----
+        home = {}       # layer -> (route index, channel offset)
+        strided_ok = ('convolutional', 'maxpool', 'upsample')
+        for i, l in enumerate(L):
+            if l['type'] == 'route' and len(l['layers_abs']) > 1 and l.get('groups', 1) == 1:
+                off = 0
+                for s in l['layers_abs']:
+                    if s not in home and L[s]['type'] in strided_ok:
+                        home[s] = (i, off)
+                    off += self.shapes[s][0]
+        bufs = {}       # route index -> tensor
+
+        def route_buf(i):
+            if i not in bufs:
+                c, h, w = self.shapes[i]
+                bufs[i] = torch.zeros(h, w, c, dtype=torch.float16, device=self.dev)
+            return bufs[i]
+
+        self.views = []     # per layer: (tensor, c, c_stride, c_off, h, w)
+        self.params = {}
+        self.heads = []
+        for i, l in enumerate(L):
+            t = l['type']
+            c, h, w = self.shapes[i]
+            if i in home:
+                ri, off = home[i]
+                out = (route_buf(ri), c, self.shapes[ri][0], off, h, w)
+            elif t in ('convolutional', 'maxpool', 'upsample', 'shortcut'):
+                out = (torch.zeros(h, w, c, dtype=torch.float16, device=self.dev), c, c, 0, h, w)
+            else:
+                out = None
+            src = self.views[i - 1] if i else (self.inp, 4, 4, 0, H, W)
+            if t == 'convolutional':
+                wt, bs = weights[i]
+                k = l['size']
+                cin = src[1]
+                if i == 0:   # physical input has 4 channels (4th is zero)
+                    wt = np.concatenate([wt, np.zeros(wt.shape[:3] + (1,), np.float32)], -1)
+                wd = torch.as_tensor(np.ascontiguousarray(wt)).to(self.dev).half().contiguous()
+                bd = torch.as_tensor(bs).to(self.dev).float().contiguous()
+                self.params[i] = (wd, bd)
+                pad = k // 2 if l.get('pad', 0) else 0
+                d = _conv_desc(1, src[4], src[5], cin, src[2], src[3], h, w, c, out[2], out[3], k, l.get('stride', 1),
+                               pad, _ACT[l.get('activation', 'linear')])
+                self._conv(d, src[0], wd, bd, out[0])
+            elif t == 'maxpool':
+                self._add('fm_maxpool', ptr(src[0]), ptr(out[0]), 1, src[4], src[5], src[1], src[2], src[3],
+                          l['size'], l['stride'], out[2], out[3])
+            elif t == 'upsample':
+                self._add('fm_upsample_copy', ptr(src[0]), ptr(out[0]), 1, src[4], src[5], src[1], src[2], src[3],
+                          l['stride'], out[2], out[3])
+            elif t == 'shortcut':
+                a, b = self.views[i - 1], self.views[l['from_abs']]
+                self._add('fm_add_act_strided', ptr(a[0]), a[2], a[3], ptr(b[0]), b[2], b[3], ptr(out[0]), out[2],
+                          out[3], h * w, c, _ACT[l.get('activation', 'linear')])
+            elif t == 'route':
+                srcs = l['layers_abs']
+                g = l.get('groups', 1)
+                if len(srcs) == 1:
+                    sv = self.views[srcs[0]]
+                    cg = sv[1] // g
+                    out = (sv[0], cg, sv[2], sv[3] + l.get('group_id', 0) * cg, sv[4], sv[5])
+                else:
+                    buf = route_buf(i)
+                    off = 0
+                    for s in srcs:
+                        sv = self.views[s]
+                        cs = sv[1] // g
+                        if home.get(s, (None,))[0] != i:
+                            self._add('fm_upsample_copy', ptr(sv[0]), ptr(buf), 1, sv[4], sv[5], cs, sv[2],
+                                      sv[3] + l.get('group_id', 0) * cs, 1, c, off)
+                        off += cs
+                    out = (buf, c, c, 0, h, w)
+            elif t == 'yolo':
+                out = self.views[i - 1]
+                assert out[2] == out[1] and out[3] == 0
+                self.heads.append(out[0])
+            self.views.append(out)
+
+    def forward(self, inp):
+        if inp.data_ptr() != self.inp.data_ptr():
+            self.inp.copy_(inp)
+        self.replay()
+        return self.heads
+
+
+def build_yolo_engine(model, weights=None, use_tc=True, use_graph=True, head_obj_bias=-5.0):
+    """Engine for a `models.YOLO` descriptor.  Without a Darknet .weights file the weights are synthetic
+    (seeded He-normal, detection-prior objectness bias) — there are no trained weights offline."""
+    if isinstance(model.CFG, str) and model.CFG in darknet.BUILDERS:
+        layers = darknet.BUILDERS[model.CFG](num_classes=model.NUM_CLASSES,
+                                             anchors_per_head=len(model.ANCHORS[0]) // 2)
+    else:
+        _, layers = darknet.parse_cfg(open(model.CFG).read())
+    if weights is None:
+        if model.WEIGHTS_PATH:
+            weights = darknet.load_weights(model.WEIGHTS_PATH, layers, 3)
+        else:
+            weights = darknet.synthetic_weights(layers, 3, head_obj_bias=head_obj_bias,
+                                                num_classes=model.NUM_CLASSES)
+    return YoloEngine(layers, model.INPUT_SHAPE[1:], weights, use_tc=use_tc, use_graph=use_graph)
+
+
+class OSNetEngine(_Net):
+    """OSNet executor for up to `max_batch` crops per call: forward(x [n,256,128,4] fp16, n) -> [n, 512] f32
+    L2-normalised embeddings (feature_extractor.py:62-74)."""
+
+    def __init__(self, width, weights=None, input_hw=(256, 128), feature_dim=512, max_batch=256, use_tc=True,
+                 use_graph=False):
+        super().__init__(use_tc, use_graph)
+        self.ops = osnet.build_osnet(width, feature_dim)
+        self.weights = weights if weights is not None else osnet.synthetic_weights(self.ops)
+        self.max_batch = max_batch
+        self.feature_dim = feature_dim
+        self.macs_per_crop = osnet.count_macs(self.ops, *input_hw)
+        B, (H, W) = max_batch, input_hw
+        dev = self.dev
+        self.inp = torch.zeros(B, H, W, 4, dtype=torch.float16, device=dev)
+        self.out = torch.zeros(B, feature_dim, dtype=torch.float32, device=dev)
+        self.n_dev = None
+        # last use of every symbolic buffer -> simple size-keyed recycling
+        last = {}
+        for k, op in enumerate(self.ops):
+            for name in self._reads(op):
+                last[name] = k
+        pool = {}
+        live = {'input': (self.inp, 4, H, W)}
+        params = {}
+
+        def alloc(numel, dtype=torch.float16):
+            key = (numel, dtype)
+            if pool.get(key):
+                return pool[key].pop()
+            return torch.zeros(numel, dtype=dtype, device=dev)
+
+        def release(name):
+            t = live.pop(name, None)
+            if t is not None and name not in ('input',):
+                pool.setdefault((t[0].numel(), t[0].dtype), []).append(t[0])
+
+        def dparam(name):
+            if name not in params:
+                params[name] = tuple(torch.as_tensor(a).to(dev) for a in self.weights[name])
+            return params[name]
+
+        self.pooled = torch.zeros(B, 512, dtype=torch.float32, device=dev)
+        self.gate_tmp = torch.zeros(B, 512, dtype=torch.float32, device=dev)
+        self._params = params
+        for k, op in enumerate(self.ops):
+            kind = op[0]
+            if kind == 'conv':
+                _, name, cin, cout, ks, stride, pad, act, src, dst = op
+                x, xc, h, w = live[src]
+                ho, wo = (h + 2 * pad - ks) // stride + 1, (w + 2 * pad - ks) // stride + 1
+                wt, bs = self.weights[name]
+                if xc != cin:  # stem: physical 4 channels
+                    wt = np.concatenate([wt, np.zeros(wt.shape[:3] + (xc - cin,), np.float32)], -1)
+                wd = torch.as_tensor(np.ascontiguousarray(wt)).to(dev).half().contiguous()
+                bd = torch.as_tensor(bs).to(dev).float().contiguous()
+                params[name] = (wd, bd)
+                y = alloc(B * ho * wo * cout)
+                d = _conv_desc(B, h, w, xc, xc, 0, ho, wo, cout, cout, 0, ks, stride, pad, _ACT[act])
+                self._conv(d, x, wd, bd, y)
+                new = (dst, (y, cout, ho, wo))
+            elif kind == 'dw':
+                _, name, c, act, src, dst = op
+                x, xc, h, w = live[src]
+                wd, bd = dparam(name)
+                wd = wd.half().contiguous()
+                params[name] = (wd, bd)
+                y = alloc(B * h * w * c)
+                self._add('fm_dwconv3', ptr(x), ptr(wd), ptr(bd), ptr(y), B, h, w, c, _ACT[act])
+                new = (dst, (y, c, h, w))
+            elif kind == 'maxpool3s2':
+                x, xc, h, w = live[op[1]]
+                ho, wo = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+                y = alloc(B * ho * wo * xc)
+                self._add('fm_maxpool_pad', ptr(x), ptr(y), B, h, w, xc, 3, 2, 1)
+                new = (op[2], (y, xc, ho, wo))
+            elif kind == 'avgpool2':
+                x, xc, h, w = live[op[1]]
+                y = alloc(B * (h // 2) * (w // 2) * xc)
+                self._add('fm_avgpool2', ptr(x), ptr(y), B, h, w, xc)
+                new = (op[2], (y, xc, h // 2, w // 2))
+            elif kind == 'gate':
+                _, name, c, src, acc, accumulate = op
+                x, xc, h, w = live[src]
+                w1, b1, w2, b2 = dparam(name)
+                if acc not in live:
+                    live[acc] = (alloc(B * h * w * c), c, h, w)
+                a = live[acc][0]
+                self._add('fm_channel_gate', ptr(x), ptr(self.pooled), ptr(self.gate_tmp), ptr(w1), ptr(b1), ptr(w2),
+                          ptr(b2), ptr(a), B, h * w, c, w1.shape[0], accumulate)
+                new = None
+            elif kind == 'add_relu':
+                a, ac, h, w = live[op[1]]
+                b = live[op[2]][0]
+                y = alloc(B * h * w * ac)
+                self._add('fm_add_act', ptr(a), ptr(b), ptr(y), B * h * w * ac, _ACT['relu'])
+                new = (op[3], (y, ac, h, w))
+            elif kind == 'gap':
+                x, xc, h, w = live[op[1]]
+                y = alloc(B * xc, torch.float32)
+                self._add('fm_global_avgpool', ptr(x), ptr(y), B, h * w, xc)
+                new = (op[2], (y, xc, 1, 1))
+            elif kind == 'fc':
+                _, name, cin, cout, src, dst = op
+                x = live[src][0]
+                wd, bd = dparam(name)
+                self._add('fm_fc_norm', ptr(x), ptr(wd), ptr(bd), ptr(self.out), B, cin, cout, 1, 1)
+                new = None
+            else:
+                raise NotImplementedError(kind)
+            for name in self._reads(op):
+                if last.get(name) == k and not (kind == 'gate' and name == op[4]):
+                    release(name)
+            if new is not None:
+                if new[0] in live:
+                    release(new[0])
+                live[new[0]] = new[1]
+
+    @staticmethod
+    def _reads(op):
+        kind = op[0]
+        if kind == 'conv':
+            return [op[8]]
+        if kind == 'dw':
+            return [op[4]]
+        if kind in ('maxpool3s2', 'avgpool2', 'gap'):
+            return [op[1]]
+        if kind == 'gate':
+            return [op[3], op[4]]
+        if kind == 'add_relu':
+            return [op[1], op[2]]
+        if kind == 'fc':
+            return [op[4]]
+        return []
+
+    def forward(self, n=None):
+        """Runs the recorded network on self.inp (all max_batch rows; rows >= n are don't-care)."""
+        self.replay()
+        return self.out if n is None else self.out[:n]
+
+
+def build_reid_engine(model, max_batch=256, use_tc=True, use_graph=True):
+    arch, width = model.ARCH
+    assert arch == 'osnet'
+    return OSNetEngine(width, input_hw=model.INPUT_SHAPE[1:], feature_dim=model.OUTPUT_LAYOUT, max_batch=max_batch,
+                       use_tc=use_tc, use_graph=use_graph)

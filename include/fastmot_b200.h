@@ -144,10 +144,10 @@ int fm_roi_resize_norm(const unsigned char* frame, int src_w, int src_h, const d
 
 /* CalDetection / CalDetection_NewCoords (fastmot/plugins/yolo_layer.cu:127-230) fused with the class mask +
  * score threshold + pixel scaling of YOLODetector._filter_dets (fastmot/detector.py:331-341).  One call per
- * head; head_out is [(5+C)*A, H, W] fp32 (is_fp16 = 0) or fp16.  Survivors write their 7-float record to
+ * head; head_out is [(5+C)*A, H, W] (nhwc = 0, the plugin's layout) or [H, W, (5+C)*A] (nhwc = 1), fp32 or fp16.  Survivors write their 7-float record to
  * dense[cand_base + idx][8] and append a sort key to keys[] (counter is incremented atomically; the caller zeroes
  * it before the first head). */
-int fm_yolo_decode_filter(const void* head_out, int is_fp16, int yolo_w, int yolo_h, int num_anchors,
+int fm_yolo_decode_filter(const void* head_out, int is_fp16, int nhwc, int yolo_w, int yolo_h, int num_anchors,
                           const FmYoloHead* h_head, int num_classes, int input_w, int input_h, int new_coords,
                           int cand_base, const unsigned char* label_mask, double conf_thresh, float size_w,
                           float size_h, float off_x, float off_y, float* dense, unsigned long long* keys,
@@ -162,6 +162,52 @@ int fm_diou_nms_filter(unsigned long long* keys, const float* dense, const int* 
                        double nms_thresh, double max_area, double min_aspect_ratio, unsigned long long* mask,
                        int max_out, double* out_tlbr, long long* out_label, double* out_conf, int* out_count,
                        int* status, void* stream);
+
+/* ---------------------------------------------------------------- conv stacks (replace the TensorRT engines) -- */
+/* The reference runs YOLO / OSNet as TensorRT engines (fastmot/utils/inference.py:39-125, built by
+ * fastmot/models/yolo.py:106-151 and reid.py:48-92).  Here the same graphs run layer by layer on NHWC fp16
+ * tensors; layer semantics follow scripts/yolo2onnx.py:558-870.  BN is folded into weight + bias by the host. */
+#define FM_ACT_LINEAR 0
+#define FM_ACT_LEAKY 1    /* alpha 0.1, yolo2onnx.py:421 */
+#define FM_ACT_MISH 2
+#define FM_ACT_SWISH 3
+#define FM_ACT_LOGISTIC 4
+#define FM_ACT_RELU 5
+
+typedef struct FmConvDesc {
+    int n, hi, wi, cin, cin_stride, cin_offset;     /* input  [n][hi][wi][cin_stride], channels [off, off+cin) */
+    int ho, wo, cout, cout_stride, cout_offset;     /* output [n][ho][wo][cout_stride], channels [off, off+cout) */
+    int kh, kw, stride, pad, act;
+    int res_stride, res_offset;                     /* optional residual added after the activation */
+} FmConvDesc;
+
+/* weights: [cout][kh][kw][cin] fp16 (K-major), bias fp32[cout] or NULL, residual fp16 or NULL. */
+int fm_conv2d_simt(const FmConvDesc* h_desc, const void* in, const void* wgt, const float* bias, const void* residual,
+                   void* out, void* stream);
+/* tcgen05 / TMEM implicit-GEMM path (csrc/conv_tc.cu); requires cin % 16 == 0, 16-byte aligned channel slices. */
+int fm_conv2d_tc(const FmConvDesc* h_desc, const void* in, const void* wgt, const float* bias, const void* residual,
+                 void* out, void* stream);
+int fm_conv2d_tc_supported(const FmConvDesc* h_desc);
+/* Darknet maxpool (SAME_UPPER, yolo2onnx.py:838-863) with channel-slice in/out; PyTorch-style padded maxpool. */
+int fm_maxpool(const void* in, void* out, int n, int hi, int wi, int c, int cin_stride, int cin_off, int k, int stride,
+               int cout_stride, int cout_off, void* stream);
+int fm_maxpool_pad(const void* in, void* out, int n, int hi, int wi, int c, int k, int stride, int pad, void* stream);
+int fm_avgpool2(const void* in, void* out, int n, int hi, int wi, int c, void* stream);
+/* nearest upsample (yolo2onnx.py:806-836) and/or route copy (:743-804): channel slice in -> channel slice out. */
+int fm_upsample_copy(const void* in, void* out, int n, int hi, int wi, int c, int cin_stride, int cin_off, int scale,
+                     int cout_stride, int cout_off, void* stream);
+int fm_add_act(const void* a, const void* b, void* out, long long n, int act, void* stream); /* shortcut :707-731 */
+int fm_add_act_strided(const void* a, int a_stride, int a_off, const void* b, int b_stride, int b_off, void* out,
+                       int o_stride, int o_off, long long pixels, int c, int act, void* stream);
+int fm_dwconv3(const void* in, const void* w, const float* bias, void* out, int n, int h, int wd, int c, int act,
+               void* stream);
+int fm_global_avgpool(const void* in, float* out, int n, int hw, int c, void* stream);
+/* OSNet channel gate: acc (+)= x * sigmoid(W2 relu(W1 GAP(x) + b1) + b2) */
+int fm_channel_gate(const void* x, float* pooled, float* gate, const float* w1, const float* b1, const float* w2,
+                    const float* b2, void* acc, int n, int hw, int c, int cr, int accumulate, void* stream);
+/* FC (+ReLU) and the row L2 normalisation of FeatureExtractor.postprocess (feature_extractor.py:73). */
+int fm_fc_norm(const float* in, const float* w, const float* bias, float* out, int n, int cin, int cout, int relu,
+               int normalize, void* stream);
 
 /* ---------------------------------------------------------------- KLT optical flow (fastmot/flow.py) ---------- */
 #define FM_NO_OWNER 0x7fffffff
