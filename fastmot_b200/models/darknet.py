@@ -283,7 +283,7 @@ def count_flops(layers, in_c, in_h, in_w):
 
 
 # ------------------------------------------------------------------------------------------------ weights
-def synthetic_weights(layers, in_c, seed_base=1000, head_obj_bias=None, num_classes=1):
+def synthetic_weights(layers, in_c, seed_base=1000, head_obj_bias=None, num_classes=1, calibrate=True):
     """Seeded He-normal conv weights (seed = seed_base + layer index) with BN folded.
     Returns {layer_index: (weight [out][kh][kw][in] float32, bias float32[out])}.
     head_obj_bias: if set, the objectness bias of every head conv (the conv right before a [yolo] layer) is
@@ -298,10 +298,15 @@ def synthetic_weights(layers, in_c, seed_base=1000, head_obj_bias=None, num_clas
         w = rng.normal(0, np.sqrt(2.0 / (k * k * cin)), (cout, k, k, cin)).astype(np.float32)
         b = rng.normal(0, 0.02, cout).astype(np.float32)
         is_head = i + 1 < len(res) and res[i + 1]['type'] == 'yolo'
-        if is_head and head_obj_bias is not None:
-            info = 5 + num_classes
-            b[4::info] = head_obj_bias
+        if is_head:
+            b[:] = 0
+            if head_obj_bias is not None:
+                info = 5 + num_classes
+                b[4::info] = head_obj_bias
         out[i] = (w, b)
+    if calibrate:
+        from .calibrate import calibrate_darknet
+        out = calibrate_darknet(res, out, in_c)
     return out
 
 

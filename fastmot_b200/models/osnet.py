@@ -70,7 +70,7 @@ def build_osnet(width=1.0, feature_dim=512):
     return ops
 
 
-def synthetic_weights(ops, seed_base=5000, reduction=16):
+def synthetic_weights(ops, seed_base=5000, reduction=16, calibrate=True):
     """Seeded He-normal weights with folded BN for every parametrised op."""
     w = {}
     k = 0
@@ -99,8 +99,11 @@ def synthetic_weights(ops, seed_base=5000, reduction=16):
             _, name, cin, cout = op[:4]
             rng = np.random.default_rng(seed_base + k)
             w[name] = (rng.normal(0, np.sqrt(2.0 / cin), (cout, cin)).astype(np.float32),
-                       rng.normal(0.05, 0.02, cout).astype(np.float32))
+                       rng.normal(0.0, 0.02, cout).astype(np.float32))
         k += 1
+    if calibrate:
+        from .calibrate import calibrate_osnet
+        w = calibrate_osnet(ops, w)
     return w
 
 
