@@ -50,6 +50,7 @@ SIGNATURES = {
     "fm_device_ok": (c_i, []),
     "fm_memcpy_async": (c_i, [c_p, c_p, c_ll, c_p]),
     "fm_host_is_pinned": (c_i, [c_p]),
+    "fm_launch_count": (c_ll, []),
     "fm_kalman_step_batched": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p,
                                       C.POINTER(FmKalmanParams), c_d, c_d, c_p, c_p, c_p]),
     "fm_kalman_create_batched": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, C.POINTER(FmKalmanParams), c_p]),
@@ -138,3 +139,17 @@ def require_device():
         raise FastMOTLibError("fastmot_b200 needs an sm_100 (B200) CUDA device: "
                               + lib.fm_last_error().decode(errors="replace"))
     return lib
+
+
+_graph_kernels = 0
+
+
+def count_graph_kernels(n):
+    """Kernels executed through CUDA-graph replays never pass the C-ABI launch sites; account for them here."""
+    global _graph_kernels
+    _graph_kernels += n
+
+
+def launch_count():
+    """Number of fastmot_b200 kernels launched so far in this process (bench.py `gpu_launches`)."""
+    return int(load().fm_launch_count()) + _graph_kernels

@@ -13,8 +13,11 @@
 
 extern "C" void fm_set_last_error(const char* msg);
 
+extern "C" void fm_count_launches(int n);
+
 #define FM_CHECK_LAUNCH(name)                                                      \
     do {                                                                           \
+        fm_count_launches(1);                                                      \
         cudaError_t e__ = cudaGetLastError();                                      \
         if (e__ != cudaSuccess) {                                                  \
             char buf__[256];                                                       \

@@ -51,3 +51,9 @@ extern "C" int fm_host_is_pinned(const void* p) {
     }
     return a.type == cudaMemoryTypeHost ? 1 : 0;
 }
+
+// Kernel-launch accounting for bench.py's `gpu_launches` (one increment per C-ABI launch site; multi-kernel entry
+// points add their extra kernels explicitly).
+static long long g_launches = 0;
+extern "C" void fm_count_launches(int n) { __atomic_fetch_add(&g_launches, (long long)n, __ATOMIC_RELAXED); }
+extern "C" long long fm_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }

@@ -64,10 +64,14 @@ class _Net:
             self.n_simt += 1
         self.launches.append(_Launch(fn, (C.byref(desc), ptr(x), ptr(w), ptr(b), ptr(residual), ptr(out)), "conv"))
 
+    def kernels_per_replay(self):
+        return sum(3 if l.what == 'fm_channel_gate' else 1 for l in self.launches)
+
     def _add(self, fn_name, *args):
         self.launches.append(_Launch(getattr(self._lib, fn_name), args, fn_name))
 
     def replay(self):
+        _lib.count_graph_kernels(self.kernels_per_replay() if self.use_graph and self._graph is not None else 0)
         if self.use_graph:
             if self._graph is None:
                 s = torch.cuda.Stream()
@@ -351,3 +355,63 @@ def build_reid_engine(model, max_batch=256, use_tc=True, use_graph=True):
     assert arch == 'osnet'
     return OSNetEngine(width, input_hw=model.INPUT_SHAPE[1:], feature_dim=model.OUTPUT_LAYOUT, max_batch=max_batch,
                        use_tc=use_tc, use_graph=use_graph)
+
+
+# ------------------------------------------------------------------------------------------------ stage profiling
+class _Profiler:
+    """CUDA-event timers around the conv stacks (recorded on the stream each stack is launched on)."""
+
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.records = []
+
+    def add(self, kind, e0, e1, flops, path):
+        self.records.append((kind, e0, e1, flops, path))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {"yolo_ms": 0.0, "osnet_ms": 0.0, "yolo_flops": 0.0, "osnet_flops": 0.0, "detector_frames": 0}
+        path = set()
+        for kind, e0, e1, flops, p in self.records:
+            out[kind + "_ms"] += e0.elapsed_time(e1)
+            out[kind + "_flops"] += flops
+            out["detector_frames"] += kind == "yolo"
+            path.add(p)
+        out["conv_path"] = "+".join(sorted(path)) if path else None
+        return out
+
+
+_PROF = None
+
+
+def enable_profiling():
+    global _PROF
+    _PROF = _Profiler()
+    return _PROF
+
+
+def _profiled(kind):
+    def deco(fn):
+        def wrapper(self, *a, **k):
+            if _PROF is None:
+                return fn(self, *a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(self, *a, **k)
+            e1.record()
+            if kind == "yolo":
+                flops = float(self.flops)
+            else:
+                n = a[0] if a and a[0] is not None else self.max_batch
+                flops = 2.0 * self.macs_per_crop * n
+            path = "tcgen05" if self.n_tc >= self.n_simt else "simt"
+            _PROF.add(kind, e0, e1, flops, f"{kind}:{path}({self.n_tc}tc/{self.n_simt}simt)")
+            return r
+        return wrapper
+    return deco
+
+
+YoloEngine.forward = _profiled("yolo")(YoloEngine.forward)
+OSNetEngine.forward = _profiled("osnet")(OSNetEngine.forward)

@@ -30,6 +30,8 @@ int fm_device_ok(void);
 /* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream) — lets the Python host move small blocks without
  * another CUDA binding. */
 int fm_memcpy_async(void* dst, const void* src, long long bytes, void* stream);
+/* kernels launched through this library so far in the process (bench.py `gpu_launches`). */
+long long fm_launch_count(void);
 /* 1 if the HOST pointer is page-locked (cudaHostAlloc / cudaHostRegister), else 0. */
 int fm_host_is_pinned(const void* h_ptr);
 
