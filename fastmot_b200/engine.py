@@ -235,11 +235,15 @@ class OSNetEngine(_Net):
         live = {'input': (self.inp, 4, H, W)}
         params = {}
 
+        self._bufs = []     # every activation buffer must outlive the recorded launches (raw pointers!)
+
         def alloc(numel, dtype=torch.float16):
             key = (numel, dtype)
             if pool.get(key):
                 return pool[key].pop()
-            return torch.zeros(numel, dtype=dtype, device=dev)
+            t = torch.zeros(numel, dtype=dtype, device=dev)
+            self._bufs.append(t)
+            return t
 
         def release(name):
             t = live.pop(name, None)
