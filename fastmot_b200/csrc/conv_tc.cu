@@ -1,12 +1,291 @@
-// tcgen05 / TMEM implicit-GEMM convolution (placeholder until the kernel lands in this round).
+// tcgen05 / TMEM implicit-GEMM convolution for sm_100a (the dense contraction of the detector and ReID stacks).
+//
+//   D[M = N*Ho*Wo pixels, Cout] = im2col(X)[M, K = kh*kw*Cin] * W^T[K, Cout],  fp16 operands, fp32 accumulate in TMEM.
+//
+// One CTA computes a 128 x BN output tile.  The K loop walks 64-element slices: all 128 threads gather the A slice
+// (128 pixels x 64 reduction elements, zero-filled at the image border) and the B slice (BN filters x 64) from
+// global memory with 16-byte loads straight into the 128-byte-swizzled K-major layout the tensor core reads, then one
+// thread issues four tcgen05.mma (UMMA 128 x BN x 16) per slice and commits them to an mbarrier.  The smem ring is
+// STAGES deep, so the gather of slice k+1.. overlaps the asynchronous MMAs of slice k; a stage is reused only after
+// its commit barrier fired.  Epilogue: each warp reads its 32 TMEM lanes with tcgen05.ld, applies bias + activation
+// (+ residual) and stores fp16 NHWC (channel-slice aware, so route/concat layers need no copy).
+//
+// Replaces the TensorRT conv tactics behind fastmot/utils/inference.py:106-117.  Descriptor bit layouts follow the
+// PTX ISA "tcgen05 matrix / instruction descriptor" tables (cross-checked against cute/arch/mma_sm100_desc.hpp).
 #include "common.cuh"
 #include "../../include/fastmot_b200.h"
 
-extern "C" int fm_conv2d_tc_supported(const FmConvDesc* d) { (void)d; return 0; }
+namespace {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;           // fp16 elements per K slice = one 128-byte swizzle row
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity));
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: start>>4 | LBO=1 | SBO=1024B | version 1 | layout 2
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=BN
+__device__ __forceinline__ uint32_t make_idesc(int bn) {
+    uint32_t d = 0;
+    d |= 1u << 4;                       // c_format = F32
+    d |= 0u << 7;                       // a_format = F16
+    d |= 0u << 10;                      // b_format = F16
+    d |= (uint32_t)(bn >> 3) << 17;     // n_dim
+    d |= (uint32_t)(TC_BM >> 4) << 24;  // m_dim
+    return d;
+}
+
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float tc_act(float v, int act) {
+    switch (act) {
+        case FM_ACT_LEAKY: return v > 0.f ? v : 0.1f * v;
+        case FM_ACT_RELU: return v > 0.f ? v : 0.f;
+        case FM_ACT_MISH: { float sp = v > 20.f ? v : log1pf(__expf(v)); return v * tanhf(sp); }
+        case FM_ACT_SWISH: return v / (1.f + __expf(-v));
+        case FM_ACT_LOGISTIC: return 1.f / (1.f + __expf(-v));
+        default: return v;
+    }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half* __restrict__ in,
+                                                       const __half* __restrict__ wgt, const float* __restrict__ bias,
+                                                       const __half* __restrict__ residual, __half* __restrict__ out) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment for the 128B swizzle atoms
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int A_BYTES = TC_BM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+    __shared__ uint64_t bar_stage[STAGES];
+    __shared__ uint64_t bar_done;
+    __shared__ uint32_t s_tmem;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
+    const int M = d.n * d.ho * d.wo;
+    const int Ktot = d.kh * d.kw * d.cin;
+    const int nk = (Ktot + TC_BK - 1) / TC_BK;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&bar_stage[s], 1);
+        mbar_init(&bar_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "r"((uint32_t)(BN < 32 ? 32 : BN)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem;
+
+    // ---- per-thread gather plan: chunk column c (16 B = 8 channels), rows (tid>>3) + 16*i ----
+    const int c = tid & 7;
+    const int rbase = tid >> 3;
+    int pn[8], ph[8], pw[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + rbase + 16 * i;
+        if (m < M) {
+            const int wo = m % d.wo, t = m / d.wo, ho = t % d.ho;
+            pn[i] = t / d.ho;
+            ph[i] = ho * d.stride - d.pad;
+            pw[i] = wo * d.stride - d.pad;
+        } else {
+            pn[i] = -1; ph[i] = 0; pw[i] = 0;
+        }
+    }
+    const uint32_t idesc = make_idesc(BN);
+
+    for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % STAGES;
+        if (kb >= STAGES) mbar_wait(&bar_stage[s], (uint32_t)(((kb / STAGES) - 1) & 1));
+        uint8_t* sA = smem + (size_t)s * STAGE_BYTES;
+        uint8_t* sB = sA + A_BYTES;
+        // reduction coordinates of this thread's 16-byte chunk
+        const int kelem = kb * TC_BK + c * 8;
+        const bool kvalid = kelem < Ktot;
+        const int tap = kvalid ? kelem / d.cin : 0;
+        const int cch = kvalid ? kelem - tap * d.cin : 0;
+        const int fr = tap / d.kw, fs = tap - fr * d.kw;
+        int4 va[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            va[i] = make_int4(0, 0, 0, 0);
+            if (kvalid && pn[i] >= 0) {
+                const int hi = ph[i] + fr, wi = pw[i] + fs;
+                if (hi >= 0 && hi < d.hi && wi >= 0 && wi < d.wi)
+                    va[i] = __ldg((const int4*)(in + (((size_t)pn[i] * d.hi + hi) * d.wi + wi) * d.cin_stride +
+                                                d.cin_offset + cch));
+            }
+        }
+        int4 vb[BN / 16];
+#pragma unroll
+        for (int i = 0; i < BN / 16; ++i) {
+            const int n = n0 + rbase + 16 * i;
+            vb[i] = (kvalid && n < d.cout) ? __ldg((const int4*)(wgt + (size_t)n * Ktot + kelem)) : make_int4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = rbase + 16 * i;
+            *(int4*)(sA + r * 128 + ((c ^ (r & 7)) << 4)) = va[i];
+        }
+#pragma unroll
+        for (int i = 0; i < BN / 16; ++i) {
+            const int r = rbase + 16 * i;
+            *(int4*)(sB + r * 128 + ((c ^ (r & 7)) << 4)) = vb[i];
+        }
+        fence_async_smem();      // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) {
+                // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the encoded start address
+                const uint64_t adesc = make_smem_desc(a_addr + k * 32);
+                const uint64_t bdesc = make_smem_desc(b_addr + k * 32);
+                mma_f16(tmem_base, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            tc_commit(&bar_stage[s]);    // fires when the MMAs reading this stage are done
+        }
+    }
+    if (tid == 0) tc_commit(&bar_done);
+    mbar_wait(&bar_done, 0);
+    tc_fence_after();
+
+    // ---- epilogue: TMEM lane = tile row ----
+    const int m = m0 + tid;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const bool vec_ok = ((d.cout_stride | d.cout_offset) & 7) == 0;
+    const bool res_vec = residual != nullptr && ((d.res_stride | d.res_offset) & 7) == 0;
+#pragma unroll 1
+    for (int j = 0; j < BN; j += 8) {
+        float v[8];
+        tmem_ld8(lane_addr + j, v);       // warp-collective: every lane executes it
+        const int n = n0 + j;
+        if (m >= M || n >= d.cout) continue;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float x = v[q] + ((bias && n + q < d.cout) ? bias[n + q] : 0.f);
+            v[q] = tc_act(x, d.act);
+        }
+        __half* op = out + (size_t)m * d.cout_stride + d.cout_offset + n;
+        if (n + 8 <= d.cout && vec_ok) {
+            if (residual) {
+                const __half* rp = residual + (size_t)m * d.res_stride + d.res_offset + n;
+                if (res_vec) {
+                    const int4 rv = *(const int4*)rp;
+                    const __half* rh = (const __half*)&rv;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] += __half2float(rh[q]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] += __half2float(rp[q]);
+                }
+            }
+            __align__(16) __half h[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) h[q] = __float2half(v[q]);
+            *(int4*)op = *(const int4*)h;
+        } else {
+            for (int q = 0; q < 8 && n + q < d.cout; ++q) {
+                float x = v[q];
+                if (residual) x += __half2float(residual[(size_t)m * d.res_stride + d.res_offset + n + q]);
+                op[q] = __float2half(x);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"((uint32_t)(BN < 32 ? 32 : BN)));
+}
+
+template <int BN, int STAGES>
+int launch_tc(const FmConvDesc* d, const void* in, const void* wgt, const float* bias, const void* residual, void* out,
+              cudaStream_t s) {
+    constexpr int smem = STAGES * (TC_BM * 128 + BN * 128) + 1024;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr = true;
+    }
+    const int M = d->n * d->ho * d->wo;
+    dim3 grid(fm_cdiv(M, TC_BM), fm_cdiv(d->cout, BN));
+    conv_tc_kernel<BN, STAGES><<<grid, 128, smem, s>>>(*d, (const __half*)in, (const __half*)wgt, bias,
+                                                       (const __half*)residual, (__half*)out);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int fm_conv2d_tc_supported(const FmConvDesc* d) {
+    if (!d) return 0;
+    if (d->cin % 8 || d->cin_stride % 8 || d->cin_offset % 8) return 0;   // 16-byte operand chunks
+    if ((long long)d->kh * d->kw * d->cin < 32) return 0;                  // not worth a tensor-core tile
+    if (d->n * d->ho * d->wo <= 0 || d->cout <= 0) return 0;
+    return 1;
+}
 
 extern "C" int fm_conv2d_tc(const FmConvDesc* d, const void* in, const void* wgt, const float* bias,
                             const void* residual, void* out, void* stream) {
-    (void)d; (void)in; (void)wgt; (void)bias; (void)residual; (void)out; (void)stream;
-    fm_set_last_error("fm_conv2d_tc: shape not supported by the tcgen05 path");
-    return FM_ERR_ARG;
+    FM_REQUIRE(d != nullptr, "fm_conv2d_tc: desc is NULL");
+    FM_REQUIRE(fm_conv2d_tc_supported(d), "fm_conv2d_tc: shape not supported by the tcgen05 path");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (d->cout <= 32) launch_tc<32, 4>(d, in, wgt, bias, residual, out, s);
+    else if (d->cout <= 64) launch_tc<64, 4>(d, in, wgt, bias, residual, out, s);
+    else launch_tc<128, 3>(d, in, wgt, bias, residual, out, s);
+    FM_CHECK_LAUNCH("fm_conv2d_tc");
+    return FM_OK;
 }
