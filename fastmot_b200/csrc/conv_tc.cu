@@ -3,11 +3,11 @@
 //   D[M = N*Ho*Wo pixels, Cout] = im2col(X)[M, K = kh*kw*Cin] * W^T[K, Cout],  fp16 operands, fp32 accumulate in TMEM.
 //
 // One CTA computes a 128 x BN output tile.  The K loop walks 64-element slices: all 128 threads gather the A slice
-// (128 pixels x 64 reduction elements, zero-filled at the image border) and the B slice (BN filters x 64) from
-// global memory with 16-byte loads straight into the 128-byte-swizzled K-major layout the tensor core reads, then one
-// thread issues four tcgen05.mma (UMMA 128 x BN x 16) per slice and commits them to an mbarrier.  The smem ring is
-// STAGES deep, so the gather of slice k+1.. overlaps the asynchronous MMAs of slice k; a stage is reused only after
-// its commit barrier fired.  Epilogue: each warp reads its 32 TMEM lanes with tcgen05.ld, applies bias + activation
+// (128 pixels x 64 reduction elements, zero-filled at the image border) and the B slice (BN filters x 64) with 16-byte
+// cp.async (LDGSTS) copies straight into the 128-byte-swizzled K-major layout the tensor core reads; one thread
+// issues four tcgen05.mma (UMMA 128 x BN x 16) per slice and commits them to an mbarrier.  The smem ring is STAGES
+// deep with STAGES-1 slices of copies in flight, so global/L2 latency and the asynchronous MMAs overlap; a stage
+// is refilled only after the commit barrier of the MMAs that read it fired.  Epilogue: each warp reads its 32 TMEM lanes with tcgen05.ld, applies bias + activation
 // (+ residual) and stores fp16 NHWC (channel-slice aware, so route/concat layers need no copy).
 //
 // Replaces the TensorRT conv tactics behind fastmot/utils/inference.py:106-117.  Descriptor bit layouts follow the
@@ -146,49 +146,63 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
     }
     const uint32_t idesc = make_idesc(BN);
 
-    for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % STAGES;
-        if (kb >= STAGES) mbar_wait(&bar_stage[s], (uint32_t)(((kb / STAGES) - 1) & 1));
-        uint8_t* sA = smem + (size_t)s * STAGE_BYTES;
+    // cp.async (LDGSTS) gather of K-slice `kb` into ring stage `st`; out-of-image / out-of-range chunks are
+    // zero-filled by passing src-size 0.
+    auto issue_loads = [&](int kb, int st) {
+        uint8_t* sA = smem + (size_t)st * STAGE_BYTES;
         uint8_t* sB = sA + A_BYTES;
-        // reduction coordinates of this thread's 16-byte chunk
         const int kelem = kb * TC_BK + c * 8;
         const bool kvalid = kelem < Ktot;
         const int tap = kvalid ? kelem / d.cin : 0;
         const int cch = kvalid ? kelem - tap * d.cin : 0;
         const int fr = tap / d.kw, fs = tap - fr * d.kw;
-        int4 va[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            va[i] = make_int4(0, 0, 0, 0);
+            const int r = rbase + 16 * i;
+            const __half* src = in;
+            uint32_t bytes = 0;
             if (kvalid && pn[i] >= 0) {
                 const int hi = ph[i] + fr, wi = pw[i] + fs;
-                if (hi >= 0 && hi < d.hi && wi >= 0 && wi < d.wi)
-                    va[i] = __ldg((const int4*)(in + (((size_t)pn[i] * d.hi + hi) * d.wi + wi) * d.cin_stride +
-                                                d.cin_offset + cch));
+                if (hi >= 0 && hi < d.hi && wi >= 0 && wi < d.wi) {
+                    src = in + (((size_t)pn[i] * d.hi + hi) * d.wi + wi) * d.cin_stride + d.cin_offset + cch;
+                    bytes = 16;
+                }
             }
-        }
-        int4 vb[BN / 16];
-#pragma unroll
-        for (int i = 0; i < BN / 16; ++i) {
-            const int n = n0 + rbase + 16 * i;
-            vb[i] = (kvalid && n < d.cout) ? __ldg((const int4*)(wgt + (size_t)n * Ktot + kelem)) : make_int4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = rbase + 16 * i;
-            *(int4*)(sA + r * 128 + ((c ^ (r & 7)) << 4)) = va[i];
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sA + r * 128 + ((c ^ (r & 7)) << 4))),
+                         "l"(src), "r"(bytes));
         }
 #pragma unroll
         for (int i = 0; i < BN / 16; ++i) {
             const int r = rbase + 16 * i;
-            *(int4*)(sB + r * 128 + ((c ^ (r & 7)) << 4)) = vb[i];
+            const int n = n0 + r;
+            const bool ok = kvalid && n < d.cout;
+            const __half* src = ok ? wgt + (size_t)n * Ktot + kelem : wgt;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sB + r * 128 + ((c ^ (r & 7)) << 4))),
+                         "l"(src), "r"(ok ? 16u : 0u));
         }
-        fence_async_smem();      // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+    };
+
+#pragma unroll
+    for (int p = 0; p < STAGES - 1; ++p) {
+        if (p < nk) issue_loads(p, p);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % STAGES;
+        const int kn = kb + STAGES - 1;
+        if (kn < nk) {
+            const int sn = kn % STAGES;
+            // the MMAs that last read stage `sn` (slice kn - STAGES) must have retired before it is overwritten
+            if (kn >= STAGES) mbar_wait(&bar_stage[sn], (uint32_t)(((kn / STAGES) - 1) & 1));
+            issue_loads(kn, sn);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");   // slice kb has landed (this thread)
+        fence_async_smem();      // make the smem writes visible to the tensor-core (async) proxy
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+            const uint32_t a_addr = smem_u32(smem + (size_t)s * STAGE_BYTES), b_addr = a_addr + A_BYTES;
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) {
                 // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the encoded start address

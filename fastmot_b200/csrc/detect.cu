@@ -9,6 +9,10 @@
 #include "common.cuh"
 #include "../../include/fastmot_b200.h"
 
+int fm_launch_nms_scan(const unsigned long long* keys, const float* dense, const int* counter, int key_cap,
+                       const unsigned long long* mask, int words, double max_area, double min_ar, int max_out,
+                       double* out_tlbr, long long* out_label, double* out_conf, int* out_count, cudaStream_t s);
+
 namespace {
 
 __device__ __forceinline__ float sigmoidf_fast(float x) { return 1.0f / (1.0f + __expf(-x)); }
@@ -267,9 +271,8 @@ extern "C" int fm_diou_nms_filter(unsigned long long* keys, const float* dense, 
     const int words = (key_cap + 63) / 64;
     nms_mask_kernel<<<FM_NUM_SMS * 8, 64, 0, s>>>(keys, dense, counter, key_cap, nms_thresh, mask, words);
     FM_CHECK_LAUNCH("nms_mask_kernel");
-    nms_scan_kernel<<<1, 32, (size_t)(words + 1) * 8, s>>>(keys, dense, counter, key_cap, mask, words, max_area,
-                                                          min_aspect_ratio, max_out, out_tlbr, out_label, out_conf,
-                                                          out_count);
+    fm_launch_nms_scan(keys, dense, counter, key_cap, mask, words, max_area, min_aspect_ratio, max_out, out_tlbr,
+                       out_label, out_conf, out_count, s);   // blocked scan, detect_nms.cu
     FM_CHECK_LAUNCH("nms_scan_kernel");
     return FM_OK;
 }

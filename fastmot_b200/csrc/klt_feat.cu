@@ -410,13 +410,16 @@ __global__ void __launch_bounds__(1024) gather_points_kernel(const float* __rest
                                                               float* __restrict__ all_pts, int* __restrict__ trk_begin,
                                                               int* __restrict__ meta, int max_pts) {
     __shared__ int s_off[1025];
+    __shared__ int s_cnt[2048];
     const int tid = threadIdx.x;
-    // serial-ish scan over tracks (n_trk <= few hundred): thread 0
+    // counts are fetched in parallel (the dependent slot -> count loads are the slow part), prefix by thread 0
+    for (int k = tid; k < n_trk && k < 2048; k += blockDim.x) s_cnt[k] = min(kp_count[slots[k]], max_kp);
+    __syncthreads();
     if (tid == 0) {
         int acc = 0;
         for (int k = 0; k < n_trk; ++k) {
             trk_begin[k] = acc;
-            acc += min(kp_count[slots[k]], max_kp);
+            acc += k < 2048 ? s_cnt[k] : min(kp_count[slots[k]], max_kp);
         }
         trk_begin[n_trk] = acc;
         int nb = *bg_count;
@@ -428,10 +431,12 @@ __global__ void __launch_bounds__(1024) gather_points_kernel(const float* __rest
     }
     __syncthreads();
     const int n_obj = s_off[0];
-    for (int k = 0; k < n_trk; ++k) {
+    // one warp per track (32 warps in flight) instead of a serial walk over the tracks
+    const int lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
+    for (int k = wid; k < n_trk; k += nwarp) {
         const int b = trk_begin[k], e = min(trk_begin[k + 1], max_pts);
         const float* src = kp_pool + (size_t)slots[k] * max_kp * 2;
-        for (int i = tid; i < (e - b) * 2; i += blockDim.x) all_pts[2 * (size_t)b + i] = src[i];
+        for (int i = lane; i < (e - b) * 2; i += 32) all_pts[2 * (size_t)b + i] = src[i];
     }
     const int nb = meta[2];
     for (int i = tid; i < nb * 2; i += blockDim.x) all_pts[2 * (size_t)n_obj + i] = bg_pts[i];

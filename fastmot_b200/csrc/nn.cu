@@ -10,6 +10,16 @@
 #include "common.cuh"
 #include "../../include/fastmot_b200.h"
 
+// 16-byte vectorised fast paths (nn_vec.cu); each returns 1 if it took the call
+int fm_vec_dwconv3(const void*, const void*, const float*, void*, int, int, int, int, int, cudaStream_t);
+int fm_vec_add_act(const void*, const void*, void*, long long, int, cudaStream_t);
+int fm_vec_add_act_strided(const void*, int, int, const void*, int, int, void*, int, int, long long, int, int, cudaStream_t);
+int fm_vec_avgpool2(const void*, void*, int, int, int, int, cudaStream_t);
+int fm_vec_maxpool(const void*, void*, int, int, int, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int fm_vec_upsample_copy(const void*, void*, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int fm_vec_gap(const void*, float*, int, int, int, cudaStream_t);
+int fm_vec_gate_apply(const void*, const float*, void*, size_t, int, size_t, int, cudaStream_t);
+
 namespace {
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -309,6 +319,11 @@ extern "C" int fm_maxpool(const void* in, void* out, int n, int hi, int wi, int 
     const int ph = max((ho - 1) * stride + k - hi, 0), pw = max((wo - 1) * stride + k - wi, 0);
     const size_t total = (size_t)n * ho * wo * c;
     if (!total) return FM_OK;
+    if (fm_vec_maxpool(in, out, n, hi, wi, c, cin_stride, cin_off, ho, wo, cout_stride, cout_off, k, stride, ph / 2,
+                       pw / 2, (cudaStream_t)stream)) {
+        FM_CHECK_LAUNCH("fm_maxpool");
+        return FM_OK;
+    }
     maxpool_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const __half*)in, (__half*)out, n, hi, wi, c,
                                                                       cin_stride, cin_off, ho, wo, cout_stride,
                                                                       cout_off, k, stride, ph / 2, pw / 2);
@@ -322,6 +337,10 @@ extern "C" int fm_maxpool_pad(const void* in, void* out, int n, int hi, int wi, 
     const int ho = (hi + 2 * pad - k) / stride + 1, wo = (wi + 2 * pad - k) / stride + 1;
     const size_t total = (size_t)n * ho * wo * c;
     if (!total) return FM_OK;
+    if (fm_vec_maxpool(in, out, n, hi, wi, c, c, 0, ho, wo, c, 0, k, stride, pad, pad, (cudaStream_t)stream)) {
+        FM_CHECK_LAUNCH("fm_maxpool_pad");
+        return FM_OK;
+    }
     maxpool_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const __half*)in, (__half*)out, n, hi, wi, c, c,
                                                                       0, ho, wo, c, 0, k, stride, pad, pad);
     FM_CHECK_LAUNCH("fm_maxpool_pad");
@@ -331,6 +350,7 @@ extern "C" int fm_maxpool_pad(const void* in, void* out, int n, int hi, int wi, 
 extern "C" int fm_avgpool2(const void* in, void* out, int n, int hi, int wi, int c, void* stream) {
     const size_t total = (size_t)n * (hi / 2) * (wi / 2) * c;
     if (!total) return FM_OK;
+    if (fm_vec_avgpool2(in, out, n, hi, wi, c, (cudaStream_t)stream)) { FM_CHECK_LAUNCH("fm_avgpool2"); return FM_OK; }
     avgpool2_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const __half*)in, (__half*)out, n, hi, wi, c);
     FM_CHECK_LAUNCH("fm_avgpool2");
     return FM_OK;
@@ -340,6 +360,11 @@ extern "C" int fm_upsample_copy(const void* in, void* out, int n, int hi, int wi
                                 int scale, int cout_stride, int cout_off, void* stream) {
     const size_t total = (size_t)n * hi * scale * wi * scale * c;
     if (!total) return FM_OK;
+    if (fm_vec_upsample_copy(in, out, n, hi, wi, c, cin_stride, cin_off, scale, cout_stride, cout_off,
+                             (cudaStream_t)stream)) {
+        FM_CHECK_LAUNCH("fm_upsample_copy");
+        return FM_OK;
+    }
     upsample_copy_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const __half*)in, (__half*)out, n, hi, wi,
                                                                             c, cin_stride, cin_off, scale, cout_stride,
                                                                             cout_off);
@@ -349,6 +374,7 @@ extern "C" int fm_upsample_copy(const void* in, void* out, int n, int hi, int wi
 
 extern "C" int fm_add_act(const void* a, const void* b, void* out, long long n, int act, void* stream) {
     if (n <= 0) return FM_OK;
+    if (fm_vec_add_act(a, b, out, n, act, (cudaStream_t)stream)) { FM_CHECK_LAUNCH("fm_add_act"); return FM_OK; }
     add_act_kernel<<<grid_for((size_t)n), 256, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b,
                                                                           (__half*)out, (size_t)n, act);
     FM_CHECK_LAUNCH("fm_add_act");
@@ -359,6 +385,7 @@ extern "C" int fm_dwconv3(const void* in, const void* w, const float* bias, void
                           int act, void* stream) {
     const size_t total = (size_t)n * h * wd * c;
     if (!total) return FM_OK;
+    if (fm_vec_dwconv3(in, w, bias, out, n, h, wd, c, act, (cudaStream_t)stream)) { FM_CHECK_LAUNCH("fm_dwconv3"); return FM_OK; }
     dwconv3_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const __half*)in, (const __half*)w, bias,
                                                                       (__half*)out, n, h, wd, c, act);
     FM_CHECK_LAUNCH("fm_dwconv3");
@@ -367,6 +394,7 @@ extern "C" int fm_dwconv3(const void* in, const void* w, const float* bias, void
 
 extern "C" int fm_global_avgpool(const void* in, float* out, int n, int hw, int c, void* stream) {
     if (n <= 0) return FM_OK;
+    if (fm_vec_gap(in, out, n, hw, c, (cudaStream_t)stream)) { FM_CHECK_LAUNCH("fm_global_avgpool"); return FM_OK; }
     gap_kernel<<<n, 256, 0, (cudaStream_t)stream>>>((const __half*)in, out, hw, c);
     FM_CHECK_LAUNCH("fm_global_avgpool");
     return FM_OK;
@@ -377,10 +405,11 @@ extern "C" int fm_channel_gate(const void* x, float* pooled, float* gate, const 
                                int accumulate, void* stream) {
     if (n <= 0) return FM_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    gap_kernel<<<n, 256, 0, s>>>((const __half*)x, pooled, hw, c);
+    if (!fm_vec_gap(x, pooled, n, hw, c, s)) gap_kernel<<<n, 256, 0, s>>>((const __half*)x, pooled, hw, c);
     gate_fc_kernel<<<n, 128, (c + cr) * sizeof(float), s>>>(pooled, w1, b1, w2, b2, gate, c, cr);
     const size_t total = (size_t)n * hw * c;
-    gate_apply_kernel<<<grid_for(total), 256, 0, s>>>((const __half*)x, gate, (__half*)acc, (size_t)hw * c, c, total,
+    if (!fm_vec_gate_apply(x, gate, acc, (size_t)hw * c, c, total, accumulate, s))
+        gate_apply_kernel<<<grid_for(total), 256, 0, s>>>((const __half*)x, gate, (__half*)acc, (size_t)hw * c, c, total,
                                                       accumulate);
     FM_CHECK_LAUNCH("fm_channel_gate");
     return FM_OK;
@@ -398,6 +427,11 @@ extern "C" int fm_fc_norm(const float* in, const float* w, const float* bias, fl
 extern "C" int fm_add_act_strided(const void* a, int a_stride, int a_off, const void* b, int b_stride, int b_off,
                                   void* out, int o_stride, int o_off, long long pixels, int c, int act, void* stream) {
     if (pixels <= 0 || c <= 0) return FM_OK;
+    if (fm_vec_add_act_strided(a, a_stride, a_off, b, b_stride, b_off, out, o_stride, o_off, pixels, c, act,
+                               (cudaStream_t)stream)) {
+        FM_CHECK_LAUNCH("fm_add_act_strided");
+        return FM_OK;
+    }
     add_act_strided_kernel<<<grid_for((size_t)pixels * c), 256, 0, (cudaStream_t)stream>>>(
         (const __half*)a, a_stride, a_off, (const __half*)b, b_stride, b_off, (__half*)out, o_stride, o_off,
         (size_t)pixels, c, act);

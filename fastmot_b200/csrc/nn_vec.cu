@@ -1,0 +1,279 @@
+// 16-byte vectorised versions of the bandwidth-bound NHWC fp16 layers (8 channels per thread).  Each `fm_vec_*`
+// returns 1 if it handled the call (all channel counts / strides / offsets multiples of 8), 0 otherwise — the
+// scalar kernels in nn.cu remain the general path.
+#include "common.cuh"
+#include "../../include/fastmot_b200.h"
+
+namespace {
+
+struct H8 { __half2 v[4]; };
+static_assert(sizeof(H8) == 16, "H8 must be 16 bytes");
+
+__device__ __forceinline__ H8 ld8(const __half* p) { return *reinterpret_cast<const H8*>(p); }
+__device__ __forceinline__ void st8(__half* p, const H8& v) { *reinterpret_cast<H8*>(p) = v; }
+__device__ __forceinline__ void to_f(const H8& h, float* f) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 t = __half22float2(h.v[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ H8 to_h(const float* f) {
+    H8 h;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h.v[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    return h;
+}
+
+__device__ __forceinline__ float act_f(float v, int act) {
+    switch (act) {
+        case FM_ACT_LEAKY: return v > 0.f ? v : 0.1f * v;
+        case FM_ACT_RELU: return v > 0.f ? v : 0.f;
+        case FM_ACT_MISH: { float sp = v > 20.f ? v : log1pf(__expf(v)); return v * tanhf(sp); }
+        case FM_ACT_SWISH: return v / (1.f + __expf(-v));
+        case FM_ACT_LOGISTIC: return 1.f / (1.f + __expf(-v));
+        default: return v;
+    }
+}
+
+// depthwise 3x3 s1 p1 + bias + act; thread = (pixel, 8-channel group)
+__global__ void __launch_bounds__(256) dwconv3_vec(const __half* __restrict__ in, const __half* __restrict__ w,
+                                                    const float* __restrict__ bias, __half* __restrict__ out, int n,
+                                                    int h, int wd, int c, int act) {
+    const int cg = c >> 3;
+    const size_t total = (size_t)n * h * wd * cg;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int g = idx % cg;
+        size_t t = idx / cg;
+        const int x = t % wd; t /= wd;
+        const int y = t % h;
+        const int b = t / h;
+        float acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = bias ? bias[g * 8 + q] : 0.f;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int yy = y + r - 1;
+            if (yy < 0 || yy >= h) continue;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const int xx = x + s - 1;
+                if (xx < 0 || xx >= wd) continue;
+                float a[8], ww[8];
+                to_f(ld8(in + (((size_t)b * h + yy) * wd + xx) * c + g * 8), a);
+                to_f(ld8(w + (size_t)(r * 3 + s) * c + g * 8), ww);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[q] += a[q] * ww[q];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = act_f(acc[q], act);
+        st8(out + idx * 8, to_h(acc));
+    }
+}
+
+// out = act(a + b), contiguous
+__global__ void __launch_bounds__(256) add_act_vec(const __half* __restrict__ a, const __half* __restrict__ b,
+                                                    __half* __restrict__ out, size_t n8, int act) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        float x[8], y[8];
+        to_f(ld8(a + i * 8), x);
+        to_f(ld8(b + i * 8), y);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) x[q] = act_f(x[q] + y[q], act);
+        st8(out + i * 8, to_h(x));
+    }
+}
+
+__global__ void __launch_bounds__(256) add_act_strided_vec(const __half* __restrict__ a, int as, int ao,
+                                                            const __half* __restrict__ b, int bs, int bo,
+                                                            __half* __restrict__ out, int os, int oo, size_t pixels,
+                                                            int c, int act) {
+    const int cg = c >> 3;
+    const size_t total = pixels * cg;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t p = i / cg;
+        const int g = (int)(i - p * cg) * 8;
+        float x[8], y[8];
+        to_f(ld8(a + p * as + ao + g), x);
+        to_f(ld8(b + p * bs + bo + g), y);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) x[q] = act_f(x[q] + y[q], act);
+        st8(out + p * os + oo + g, to_h(x));
+    }
+}
+
+__global__ void __launch_bounds__(256) avgpool2_vec(const __half* __restrict__ in, __half* __restrict__ out, int n,
+                                                     int hi, int wi, int c) {
+    const int ho = hi / 2, wo = wi / 2, cg = c >> 3;
+    const size_t total = (size_t)n * ho * wo * cg;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int g = idx % cg;
+        size_t t = idx / cg;
+        const int x = t % wo; t /= wo;
+        const int y = t % ho;
+        const int b = t / ho;
+        const __half* p = in + (((size_t)b * hi + 2 * y) * wi + 2 * x) * c + g * 8;
+        float a0[8], a1[8], a2[8], a3[8];
+        to_f(ld8(p), a0); to_f(ld8(p + c), a1); to_f(ld8(p + (size_t)wi * c), a2); to_f(ld8(p + (size_t)wi * c + c), a3);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) a0[q] = 0.25f * (a0[q] + a1[q] + a2[q] + a3[q]);
+        st8(out + idx * 8, to_h(a0));
+    }
+}
+
+__global__ void __launch_bounds__(256) maxpool_vec(const __half* __restrict__ in, __half* __restrict__ out, int n,
+                                                    int hi, int wi, int c, int cis, int cio, int ho, int wo, int cos,
+                                                    int coo, int k, int stride, int plh, int plw) {
+    const int cg = c >> 3;
+    const size_t total = (size_t)n * ho * wo * cg;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int g = idx % cg;
+        size_t t = idx / cg;
+        const int x = t % wo; t /= wo;
+        const int y = t % ho;
+        const int b = t / ho;
+        float best[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) best[q] = -INFINITY;
+        for (int r = 0; r < k; ++r) {
+            const int yy = y * stride - plh + r;
+            if (yy < 0 || yy >= hi) continue;
+            for (int s = 0; s < k; ++s) {
+                const int xx = x * stride - plw + s;
+                if (xx < 0 || xx >= wi) continue;
+                float a[8];
+                to_f(ld8(in + (((size_t)b * hi + yy) * wi + xx) * cis + cio + g * 8), a);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) best[q] = fmaxf(best[q], a[q]);
+            }
+        }
+        st8(out + (((size_t)b * ho + y) * wo + x) * cos + coo + g * 8, to_h(best));
+    }
+}
+
+__global__ void __launch_bounds__(256) upsample_copy_vec(const __half* __restrict__ in, __half* __restrict__ out, int n,
+                                                          int hi, int wi, int c, int cis, int cio, int s, int cos,
+                                                          int coo) {
+    const int ho = hi * s, wo = wi * s, cg = c >> 3;
+    const size_t total = (size_t)n * ho * wo * cg;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int g = idx % cg;
+        size_t t = idx / cg;
+        const int x = t % wo; t /= wo;
+        const int y = t % ho;
+        const int b = t / ho;
+        st8(out + (((size_t)b * ho + y) * wo + x) * cos + coo + g * 8,
+            ld8(in + (((size_t)b * hi + y / s) * wi + x / s) * cis + cio + g * 8));
+    }
+}
+
+// global average pool: one CTA per (sample, 64-channel slab); lanes over channel groups, warps over pixels
+__global__ void __launch_bounds__(256) gap_vec(const __half* __restrict__ in, float* __restrict__ out, int hw, int c) {
+    __shared__ float s_acc[32][65];
+    const int b = blockIdx.x, slab = blockIdx.y;
+    const int c0 = slab * 64;
+    const int cgs = min(64, c - c0) >> 3;          // channel groups in this slab (<= 8)
+    const int tid = threadIdx.x;
+    const int g = tid % 8, prow = tid / 8;         // 32 pixel rows
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    if (g < cgs) {
+        const __half* p = in + (size_t)b * hw * c + c0 + g * 8;
+        for (int i = prow; i < hw; i += 32) {
+            float a[8];
+            to_f(ld8(p + (size_t)i * c), a);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] += a[q];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s_acc[prow][g * 8 + q] = acc[q];
+    __syncthreads();
+    if (tid < 64 && c0 + tid < c) {
+        float a = 0.f;
+        for (int r = 0; r < 32; ++r) a += s_acc[r][tid];
+        out[(size_t)b * c + c0 + tid] = a / hw;
+    }
+}
+
+__global__ void __launch_bounds__(256) gate_apply_vec(const __half* __restrict__ x, const float* __restrict__ gate,
+                                                       __half* __restrict__ acc, size_t per_sample, int c, size_t total8,
+                                                       int accumulate) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t e = i * 8;
+        const int ch = e % c;
+        const size_t b = e / per_sample;
+        float v[8], a[8];
+        to_f(ld8(x + e), v);
+        const float* gp = gate + b * c + ch;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] *= gp[q];
+        if (accumulate) {
+            to_f(ld8(acc + e), a);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] += a[q];
+        }
+        st8(acc + e, to_h(v));
+    }
+}
+
+inline int vgrid(size_t total, int block = 256) {
+    size_t g = (total + block - 1) / block;
+    size_t cap = (size_t)FM_NUM_SMS * 32;
+    return (int)(g < cap ? (g ? g : 1) : cap);
+}
+inline bool al8(int v) { return (v & 7) == 0; }
+
+}  // namespace
+
+int fm_vec_dwconv3(const void* in, const void* w, const float* bias, void* out, int n, int h, int wd, int c, int act,
+                   cudaStream_t s) {
+    if (!al8(c)) return 0;
+    const size_t total = (size_t)n * h * wd * (c >> 3);
+    dwconv3_vec<<<vgrid(total), 256, 0, s>>>((const __half*)in, (const __half*)w, bias, (__half*)out, n, h, wd, c, act);
+    return 1;
+}
+int fm_vec_add_act(const void* a, const void* b, void* out, long long n, int act, cudaStream_t s) {
+    if (n & 7) return 0;
+    add_act_vec<<<vgrid((size_t)n >> 3), 256, 0, s>>>((const __half*)a, (const __half*)b, (__half*)out, (size_t)n >> 3, act);
+    return 1;
+}
+int fm_vec_add_act_strided(const void* a, int as, int ao, const void* b, int bs, int bo, void* out, int os, int oo,
+                           long long pixels, int c, int act, cudaStream_t s) {
+    if (!(al8(as) && al8(ao) && al8(bs) && al8(bo) && al8(os) && al8(oo) && al8(c))) return 0;
+    add_act_strided_vec<<<vgrid((size_t)pixels * (c >> 3)), 256, 0, s>>>((const __half*)a, as, ao, (const __half*)b, bs,
+                                                                        bo, (__half*)out, os, oo, (size_t)pixels, c, act);
+    return 1;
+}
+int fm_vec_avgpool2(const void* in, void* out, int n, int hi, int wi, int c, cudaStream_t s) {
+    if (!al8(c)) return 0;
+    avgpool2_vec<<<vgrid((size_t)n * (hi / 2) * (wi / 2) * (c >> 3)), 256, 0, s>>>((const __half*)in, (__half*)out, n, hi,
+                                                                                  wi, c);
+    return 1;
+}
+int fm_vec_maxpool(const void* in, void* out, int n, int hi, int wi, int c, int cis, int cio, int ho, int wo, int cos,
+                   int coo, int k, int stride, int plh, int plw, cudaStream_t s) {
+    if (!(al8(c) && al8(cis) && al8(cio) && al8(cos) && al8(coo))) return 0;
+    maxpool_vec<<<vgrid((size_t)n * ho * wo * (c >> 3)), 256, 0, s>>>((const __half*)in, (__half*)out, n, hi, wi, c, cis,
+                                                                     cio, ho, wo, cos, coo, k, stride, plh, plw);
+    return 1;
+}
+int fm_vec_upsample_copy(const void* in, void* out, int n, int hi, int wi, int c, int cis, int cio, int sc, int cos,
+                         int coo, cudaStream_t s) {
+    if (!(al8(c) && al8(cis) && al8(cio) && al8(cos) && al8(coo))) return 0;
+    upsample_copy_vec<<<vgrid((size_t)n * hi * sc * wi * sc * (c >> 3)), 256, 0, s>>>(
+        (const __half*)in, (__half*)out, n, hi, wi, c, cis, cio, sc, cos, coo);
+    return 1;
+}
+int fm_vec_gap(const void* in, float* out, int n, int hw, int c, cudaStream_t s) {
+    if (!al8(c)) return 0;
+    dim3 grid(n, (c + 63) / 64);
+    gap_vec<<<grid, 256, 0, s>>>((const __half*)in, out, hw, c);
+    return 1;
+}
+int fm_vec_gate_apply(const void* x, const float* gate, void* acc, size_t per_sample, int c, size_t total, int accumulate,
+                      cudaStream_t s) {
+    if (!al8(c)) return 0;
+    gate_apply_vec<<<vgrid(total >> 3), 256, 0, s>>>((const __half*)x, gate, (__half*)acc, per_sample, c, total >> 3,
+                                                     accumulate);
+    return 1;
+}

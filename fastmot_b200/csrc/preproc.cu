@@ -5,22 +5,26 @@
 //                          normalisation, all crops in one launch (fastmot/feature_extractor.py:48-60, 84-98;
 //                          fastmot/utils/rect.py:92-97)
 // Outputs are either fp32 planar CHW (the reference's TensorRT input layout; used for parity tests) or fp16
-// NHWC with C padded to 4 (what the conv engine consumes).
+// NHWC with C padded to 8 (one 16-byte chunk per pixel; what the conv engine consumes).
 #include "common.cuh"
 #include "../../include/fastmot_b200.h"
 
 namespace {
 
-template <int LAYOUT>  // 0: fp32 CHW, 1: fp16 NHWC4
+template <int LAYOUT>  // 0: fp32 CHW, 1: fp16 NHWC8
 __device__ __forceinline__ void store_px(void* out, int H, int W, int y, int x, float r, float g, float b) {
     if (LAYOUT == 0) {
         float* o = (float*)out;
         size_t plane = (size_t)H * W, p = (size_t)y * W + x;
         o[p] = r; o[plane + p] = g; o[2 * plane + p] = b;
     } else {
-        __half2* o = (__half2*)out + ((size_t)y * W + x) * 2;
-        o[0] = __floats2half2_rn(r, g);
-        o[1] = __floats2half2_rn(b, 0.0f);
+        // 8 channels = one 16-byte chunk per pixel: the tcgen05 conv gathers operands in 16-byte units
+        __align__(16) __half2 v[4];
+        v[0] = __floats2half2_rn(r, g);
+        v[1] = __floats2half2_rn(b, 0.0f);
+        v[2] = __floats2half2_rn(0.0f, 0.0f);
+        v[3] = v[2];
+        *reinterpret_cast<int4*>((__half*)out + ((size_t)y * W + x) * 8) = *reinterpret_cast<const int4*>(v);
     }
 }
 
@@ -107,7 +111,7 @@ __global__ void __launch_bounds__(128) roi_resize_norm_kernel(const unsigned cha
         v[c] = (float)(((double)px / 255.0 - (double)mean[c]) / (double)stdv[c]);
     }
     void* o = LAYOUT == 0 ? (void*)((float*)out + (size_t)crop * 3 * out_h * out_w)
-                          : (void*)((__half*)out + (size_t)crop * 4 * out_h * out_w);
+                          : (void*)((__half*)out + (size_t)crop * 8 * out_h * out_w);
     store_px<LAYOUT>(o, out_h, out_w, y, x, v[2], v[1], v[0]);
 }
 
@@ -115,7 +119,7 @@ __global__ void __launch_bounds__(128) roi_resize_norm_kernel(const unsigned cha
 
 extern "C" int fm_letterbox_preproc(const unsigned char* frame, int src_w, int src_h, int dst_w, int dst_h,
                                     int roi_x, int roi_y, int roi_w, int roi_h, int layout, void* out, void* stream) {
-    FM_REQUIRE(layout == 0 || layout == 1, "fm_letterbox_preproc: layout must be 0 (f32 CHW) or 1 (f16 NHWC4)");
+    FM_REQUIRE(layout == 0 || layout == 1, "fm_letterbox_preproc: layout must be 0 (f32 CHW) or 1 (f16 NHWC8)");
     FM_REQUIRE(roi_w > 0 && roi_h > 0, "fm_letterbox_preproc: empty ROI");
     dim3 grid(fm_cdiv(dst_w, 256), dst_h);
     if (layout == 0)
@@ -131,7 +135,7 @@ extern "C" int fm_letterbox_preproc(const unsigned char* frame, int src_w, int s
 extern "C" int fm_roi_resize_norm(const unsigned char* frame, int src_w, int src_h, const double* tlbrs,
                                   const int* n_dev, int n_max, int out_w, int out_h, int layout, void* out,
                                   void* stream) {
-    FM_REQUIRE(layout == 0 || layout == 1, "fm_roi_resize_norm: layout must be 0 (f32 CHW) or 1 (f16 NHWC4)");
+    FM_REQUIRE(layout == 0 || layout == 1, "fm_roi_resize_norm: layout must be 0 (f32 CHW) or 1 (f16 NHWC8)");
     if (n_max <= 0) return FM_OK;
     FM_REQUIRE(n_max <= 65535, "fm_roi_resize_norm: more than 65535 crops");
     dim3 grid(fm_cdiv(out_w, 128), out_h, n_max);

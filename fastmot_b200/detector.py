@@ -120,7 +120,7 @@ class YOLODetector(Detector):
         self._h_label = torch.zeros(max_dets, dtype=torch.int64).pin_memory()
         self._h_conf = torch.zeros(max_dets, dtype=torch.float64).pin_memory()
         self._h_meta = torch.zeros(4, dtype=torch.int32).pin_memory()
-        self.inp = torch.zeros(in_h, in_w, 4, dtype=torch.float16, device=dev)   # NHWC4
+        self.inp = torch.zeros(in_h, in_w, 8, dtype=torch.float16, device=dev)   # NHWC8
         self._uploader = FrameUploader(size)
         self.frame_dev = None
         self._done = torch.cuda.Event()

@@ -15,6 +15,7 @@ from .devmem import ptr, stream_ptr
 from .models import darknet, osnet
 
 _ACT = darknet.ACTS
+IN_C_PAD = 8      # network inputs are NHWC with 3 real + 5 zero channels: one 16-byte chunk per pixel
 
 
 class _Launch:
@@ -95,14 +96,14 @@ class _Net:
 
 
 class YoloEngine(_Net):
-    """Darknet graph executor.  forward(inp NHWC4 fp16) -> list of head tensors [H, W, (5+C)*A] fp16."""
+    """Darknet graph executor.  forward(inp NHWC8 fp16) -> list of head tensors [H, W, (5+C)*A] fp16."""
     heads_nhwc = True
 
     def __init__(self, layers, input_hw, weights, use_tc=True, use_graph=False):
         super().__init__(use_tc, use_graph)
         H, W = input_hw
         self.layers, self.shapes = darknet.infer_shapes(layers, 3, H, W)
-        self.inp = torch.zeros(H, W, 4, dtype=torch.float16, device=self.dev)
+        self.inp = torch.zeros(H, W, IN_C_PAD, dtype=torch.float16, device=self.dev)
         self.flops = darknet.count_flops(layers, 3, H, W)
         L = self.layers
         n = len(L)
@@ -137,13 +138,13 @@ class YoloEngine(_Net):
                 out = (torch.zeros(h, w, c, dtype=torch.float16, device=self.dev), c, c, 0, h, w)
             else:
                 out = None
-            src = self.views[i - 1] if i else (self.inp, 4, 4, 0, H, W)
+            src = self.views[i - 1] if i else (self.inp, IN_C_PAD, IN_C_PAD, 0, H, W)
             if t == 'convolutional':
                 wt, bs = weights[i]
                 k = l['size']
                 cin = src[1]
-                if i == 0:   # physical input has 4 channels (4th is zero)
-                    wt = np.concatenate([wt, np.zeros(wt.shape[:3] + (1,), np.float32)], -1)
+                if i == 0:   # physical input has IN_C_PAD channels (the extra ones are zero)
+                    wt = np.concatenate([wt, np.zeros(wt.shape[:3] + (IN_C_PAD - wt.shape[3],), np.float32)], -1)
                 wd = torch.as_tensor(np.ascontiguousarray(wt)).to(self.dev).half().contiguous()
                 bd = torch.as_tensor(bs).to(self.dev).float().contiguous()
                 self.params[i] = (wd, bd)
@@ -210,7 +211,7 @@ def build_yolo_engine(model, weights=None, use_tc=True, use_graph=True, head_obj
 
 
 class OSNetEngine(_Net):
-    """OSNet executor for up to `max_batch` crops per call: forward(x [n,256,128,4] fp16, n) -> [n, 512] f32
+    """OSNet executor for up to `max_batch` crops per call: forward(x [n,256,128,8] fp16, n) -> [n, 512] f32
     L2-normalised embeddings (feature_extractor.py:62-74)."""
 
     def __init__(self, width, weights=None, input_hw=(256, 128), feature_dim=512, max_batch=256, use_tc=True,
@@ -223,7 +224,7 @@ class OSNetEngine(_Net):
         self.macs_per_crop = osnet.count_macs(self.ops, *input_hw)
         B, (H, W) = max_batch, input_hw
         dev = self.dev
-        self.inp = torch.zeros(B, H, W, 4, dtype=torch.float16, device=dev)
+        self.inp = torch.zeros(B, H, W, IN_C_PAD, dtype=torch.float16, device=dev)
         self.out = torch.zeros(B, feature_dim, dtype=torch.float32, device=dev)
         self.n_dev = None
         # last use of every symbolic buffer -> simple size-keyed recycling
@@ -232,7 +233,7 @@ class OSNetEngine(_Net):
             for name in self._reads(op):
                 last[name] = k
         pool = {}
-        live = {'input': (self.inp, 4, H, W)}
+        live = {'input': (self.inp, IN_C_PAD, H, W)}
         params = {}
 
         self._bufs = []     # every activation buffer must outlive the recorded launches (raw pointers!)

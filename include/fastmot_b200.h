@@ -133,14 +133,14 @@ typedef struct FmYoloHead {
 /* YOLODetector._preprocess + _create_letterbox (fastmot/detector.py:289-320): bilinear resize of the BGR u8 HWC
  * frame into the ROI [roi_x, roi_y, roi_w, roi_h] of a dst_w x dst_h network input (half-pixel centres, edge
  * replicate, rounded to u8 like the reference's CuPy zoom), BGR->RGB, x/255; everything outside the ROI = 0.5.
- * layout 0: fp32 planar CHW (the reference's TensorRT input); layout 1: fp16 NHWC, C padded to 4. */
+ * layout 0: fp32 planar CHW (the reference's TensorRT input); layout 1: fp16 NHWC, C padded to 8 (16 bytes per pixel). */
 int fm_letterbox_preproc(const unsigned char* frame, int src_w, int src_h, int dst_w, int dst_h, int roi_x, int roi_y,
                          int roi_w, int roi_h, int layout, void* out, void* stream);
 
 /* FeatureExtractor.extract_async preprocessing (fastmot/feature_extractor.py:48-60, 84-98; rect.py:92-97) for all
  * crops in one launch: integer-truncated clamp crop, OpenCV INTER_LINEAR 8-bit fixed-point resize to
  * out_w x out_h, BGR->RGB, (x/255 - mean)/std.  n = min(*n_dev, n_max) if n_dev != NULL else n_max.
- * layout as above; output is [n][3][out_h][out_w] f32 or [n][out_h][out_w][4] f16. */
+ * layout as above; output is [n][3][out_h][out_w] f32 or [n][out_h][out_w][8] f16. */
 int fm_roi_resize_norm(const unsigned char* frame, int src_w, int src_h, const double* tlbrs, const int* n_dev,
                        int n_max, int out_w, int out_h, int layout, void* out, void* stream);
 

@@ -151,11 +151,11 @@ def test_letterbox_preproc(model_name):
     diff = np.abs(got - want) * 255
     assert diff.max() <= 1.0 + 1e-3            # reference semantics pinned only to +-1 LSB (CuPy absent)
     assert (diff < 1e-3).mean() > 0.999
-    out16 = torch.zeros(H, W, 4, dtype=torch.float16, device="cuda")
+    out16 = torch.zeros(H, W, 8, dtype=torch.float16, device="cuda")
     _lib.check(lib.fm_letterbox_preproc(ptr(fd), 1920, 1080, W, H, *roi, 1, ptr(out16), stream_ptr()), "lb")
     g16 = out16.cpu().float().numpy()
     assert np.abs(g16[..., :3].transpose(2, 0, 1) - got).max() <= 1e-3
-    assert np.all(g16[..., 3] == 0)
+    assert np.all(g16[..., 3:] == 0)
 
 
 def test_roi_resize_norm():
@@ -183,7 +183,7 @@ def test_roi_resize_norm():
     assert (lsb < 1e-2).mean() > 0.99
     exact = detect.roi_preprocess_fixedpoint(frame, tl)      # the formula the kernel implements
     np.testing.assert_allclose(got, exact, atol=2e-6)
-    out16 = torch.zeros(n, 256, 128, 4, dtype=torch.float16, device="cuda")
+    out16 = torch.zeros(n, 256, 128, 8, dtype=torch.float16, device="cuda")
     _lib.check(lib.fm_roi_resize_norm(ptr(fd), 1920, 1080, ptr(td), None, n, 128, 256, 1, ptr(out16),
                                       stream_ptr()), "roi")
     g16 = out16.cpu().float().numpy()[..., :3].transpose(0, 3, 1, 2)

@@ -16,11 +16,12 @@ def _rel(got, want):
 
 CONV_CASES = [
     # n, h, w, cin, cout, k, stride, act, cin_stride, cin_off, cout_stride, cout_off, residual
-    (1, 40, 40, 4, 32, 3, 2, 'leaky', 4, 0, 32, 0, False),
+    (1, 40, 40, 8, 32, 3, 2, 'leaky', 8, 0, 32, 0, False),
     (1, 33, 29, 64, 64, 3, 1, 'mish', 64, 0, 64, 0, False),
     (2, 16, 24, 32, 48, 1, 1, 'linear', 96, 32, 80, 16, False),
     (1, 20, 20, 128, 256, 3, 2, 'leaky', 128, 0, 256, 0, False),
-    (3, 32, 16, 4, 16, 7, 2, 'relu', 4, 0, 16, 0, False),
+    (3, 32, 16, 8, 16, 7, 2, 'relu', 8, 0, 16, 0, False),
+    (1, 30, 30, 4, 16, 3, 1, 'relu', 4, 0, 16, 0, False),
     (1, 26, 26, 256, 18, 1, 1, 'logistic', 256, 0, 18, 0, False),
     (1, 24, 24, 64, 64, 3, 1, 'relu', 64, 0, 64, 0, True),
     (4, 64, 32, 16, 16, 1, 1, 'swish', 16, 0, 16, 0, False),
@@ -94,7 +95,7 @@ def _yolo_vs_oracle(name, hw, tol):
     eng = YoloEngine(layers, hw, weights, use_graph=False)
     g = torch.Generator().manual_seed(1)
     x = torch.rand(1, 3, hw[0], hw[1], generator=g)
-    inp = torch.zeros(hw[0], hw[1], 4, dtype=torch.float16)
+    inp = torch.zeros(hw[0], hw[1], 8, dtype=torch.float16)
     inp[..., :3] = x[0].permute(1, 2, 0).half()
     heads = eng.forward(inp.cuda())
     torch.cuda.synchronize()
@@ -123,8 +124,8 @@ def test_deep_yolo_engine_layerwise(name, hw):
     layers = darknet.BUILDERS[name]()
     weights = darknet.synthetic_weights(layers, 3, head_obj_bias=-3.0)
     eng = YoloEngine(layers, hw, weights, use_graph=False)
-    x = torch.rand(hw[0], hw[1], 4).half()
-    x[..., 3] = 0
+    x = torch.rand(hw[0], hw[1], 8).half()
+    x[..., 3:] = 0
     eng.forward(x.cuda())
     torch.cuda.synchronize()
 
@@ -172,7 +173,7 @@ def test_yolo_engine_graph_replay_matches_eager():
     weights = darknet.synthetic_weights(layers, 3)
     a = YoloEngine(layers, (416, 416), weights, use_graph=False)
     b = YoloEngine(layers, (416, 416), weights, use_graph=True)
-    x = torch.rand(416, 416, 4, device="cuda").half()
+    x = torch.rand(416, 416, 8, device="cuda").half()
     ha = [h.clone() for h in a.forward(x)]
     for _ in range(3):
         hb = b.forward(x)
@@ -188,7 +189,7 @@ def test_osnet_engine_vs_oracle(width):
     eng = OSNetEngine(width, max_batch=6, use_graph=False)
     g = torch.Generator().manual_seed(2)
     x = torch.randn(6, 3, 256, 128, generator=g)
-    inp = torch.zeros(6, 256, 128, 4, dtype=torch.float16)
+    inp = torch.zeros(6, 256, 128, 8, dtype=torch.float16)
     inp[..., :3] = x.permute(0, 2, 3, 1).half()
     eng.inp.copy_(inp.cuda())
     got = eng.forward().cpu()
