@@ -83,6 +83,22 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+        "%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 __device__ __forceinline__ float tc_act(float v, int act) {
     switch (act) {
         case FM_ACT_LEAKY: return v > 0.f ? v : 0.1f * v;
@@ -97,7 +113,8 @@ __device__ __forceinline__ float tc_act(float v, int act) {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half* __restrict__ in,
                                                        const __half* __restrict__ wgt, const float* __restrict__ bias,
-                                                       const __half* __restrict__ residual, __half* __restrict__ out) {
+                                                       const __half* __restrict__ residual, __half* __restrict__ out,
+                                                       float* __restrict__ ws, int slices_per_split) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B swizzle atoms
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -110,7 +127,10 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
     const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
     const int M = d.n * d.ho * d.wo;
     const int Ktot = d.kh * d.kw * d.cin;
-    const int nk = (Ktot + TC_BK - 1) / TC_BK;
+    const int nk_total = (Ktot + TC_BK - 1) / TC_BK;
+    // split-K: blockIdx.z owns K slices [kb0, kb0 + nk); partial sums go to the fp32 workspace
+    const int kb0 = blockIdx.z * slices_per_split;
+    const int nk = min(nk_total - kb0, slices_per_split);
 
     if (tid == 0) {
 #pragma unroll
@@ -151,7 +171,7 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
     auto issue_loads = [&](int kb, int st) {
         uint8_t* sA = smem + (size_t)st * STAGE_BYTES;
         uint8_t* sB = sA + A_BYTES;
-        const int kelem = kb * TC_BK + c * 8;
+        const int kelem = (kb0 + kb) * TC_BK + c * 8;
         const bool kvalid = kelem < Ktot;
         const int tap = kvalid ? kelem / d.cin : 0;
         const int cch = kvalid ? kelem - tap * d.cin : 0;
@@ -223,39 +243,51 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
     const bool vec_ok = ((d.cout_stride | d.cout_offset) & 7) == 0;
     const bool res_vec = residual != nullptr && ((d.res_stride | d.res_offset) & 7) == 0;
 #pragma unroll 1
-    for (int j = 0; j < BN; j += 8) {
-        float v[8];
-        tmem_ld8(lane_addr + j, v);       // warp-collective: every lane executes it
-        const int n = n0 + j;
-        if (m >= M || n >= d.cout) continue;
+    for (int j0 = 0; j0 < BN; j0 += 32) {
+        float v32[32];
+        tmem_ld32(lane_addr + j0, v32);   // warp-collective: every lane executes it
+        if (m >= M) continue;
+        if (gridDim.z > 1) {              // raw fp32 partials; bias / activation happen in splitk_reduce_kernel
+            float* wp = ws + ((size_t)blockIdx.z * M + m) * d.cout + n0 + j0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            float x = v[q] + ((bias && n + q < d.cout) ? bias[n + q] : 0.f);
-            v[q] = tc_act(x, d.act);
+            for (int q = 0; q < 32; ++q)
+                if (n0 + j0 + q < d.cout) wp[q] = v32[q];
+            continue;
         }
-        __half* op = out + (size_t)m * d.cout_stride + d.cout_offset + n;
-        if (n + 8 <= d.cout && vec_ok) {
-            if (residual) {
-                const __half* rp = residual + (size_t)m * d.res_stride + d.res_offset + n;
-                if (res_vec) {
-                    const int4 rv = *(const int4*)rp;
-                    const __half* rh = (const __half*)&rv;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) v[q] += __half2float(rh[q]);
-                } else {
+        for (int jj = 0; jj < 32; jj += 8) {
+            const int n = n0 + j0 + jj;
+            if (n >= d.cout) break;
+            float* v = v32 + jj;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) v[q] += __half2float(rp[q]);
-                }
+            for (int q = 0; q < 8; ++q) {
+                float x = v[q] + ((bias && n + q < d.cout) ? bias[n + q] : 0.f);
+                v[q] = tc_act(x, d.act);
             }
-            __align__(16) __half h[8];
+            __half* op = out + (size_t)m * d.cout_stride + d.cout_offset + n;
+            if (n + 8 <= d.cout && vec_ok) {
+                if (residual) {
+                    const __half* rp = residual + (size_t)m * d.res_stride + d.res_offset + n;
+                    if (res_vec) {
+                        const int4 rv = *(const int4*)rp;
+                        const __half* rh = (const __half*)&rv;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) h[q] = __float2half(v[q]);
-            *(int4*)op = *(const int4*)h;
-        } else {
-            for (int q = 0; q < 8 && n + q < d.cout; ++q) {
-                float x = v[q];
-                if (residual) x += __half2float(residual[(size_t)m * d.res_stride + d.res_offset + n + q]);
-                op[q] = __float2half(x);
+                        for (int q = 0; q < 8; ++q) v[q] += __half2float(rh[q]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] += __half2float(rp[q]);
+                    }
+                }
+                __align__(16) __half h[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) h[q] = __float2half(v[q]);
+                *(int4*)op = *(const int4*)h;
+            } else {
+                for (int q = 0; q < 8 && n + q < d.cout; ++q) {
+                    float x = v[q];
+                    if (residual) x += __half2float(residual[(size_t)m * d.res_stride + d.res_offset + n + q]);
+                    op[q] = __float2half(x);
+                }
             }
         }
     }
@@ -265,6 +297,26 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "r"((uint32_t)(BN < 32 ? 32 : BN)));
 }
+
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(FmConvDesc d, const float* __restrict__ ws, int splits,
+                                                             const float* __restrict__ bias,
+                                                             const __half* __restrict__ residual,
+                                                             __half* __restrict__ out) {
+    const int M = d.n * d.ho * d.wo;
+    const size_t total = (size_t)M * d.cout;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t m = i / d.cout;
+        const int n = (int)(i - m * d.cout);
+        float acc = 0.f;
+        for (int z = 0; z < splits; ++z) acc += ws[(size_t)z * total + i];
+        float v = tc_act(acc + (bias ? bias[n] : 0.f), d.act);
+        if (residual) v += __half2float(residual[m * d.res_stride + d.res_offset + n]);
+        out[m * d.cout_stride + d.cout_offset + n] = __float2half(v);
+    }
+}
+
+float* g_ws = nullptr;
+long long g_ws_bytes = 0;
 
 template <int BN, int STAGES>
 int launch_tc(const FmConvDesc* d, const void* in, const void* wgt, const float* bias, const void* residual, void* out,
@@ -276,13 +328,38 @@ int launch_tc(const FmConvDesc* d, const void* in, const void* wgt, const float*
         attr = true;
     }
     const int M = d->n * d->ho * d->wo;
-    dim3 grid(fm_cdiv(M, TC_BM), fm_cdiv(d->cout, BN));
+    const int nk = (d->kh * d->kw * d->cin + TC_BK - 1) / TC_BK;
+    dim3 grid(fm_cdiv(M, TC_BM), fm_cdiv(d->cout, BN), 1);
+    int sps = nk;
+    // split-K when the output tiling alone cannot fill the 148 SMs (batch-1 deep layers)
+    const int tiles = grid.x * grid.y;
+    if (g_ws && tiles * 2 <= FM_NUM_SMS && nk >= 8) {
+        int want = (FM_NUM_SMS + tiles - 1) / tiles;
+        if (want > nk / 4) want = nk / 4;
+        if (want > 1) {
+            sps = (nk + want - 1) / want;
+            const int splits = (nk + sps - 1) / sps;
+            if ((long long)splits * M * d->cout * 4 <= g_ws_bytes) grid.z = splits; else sps = nk;
+        }
+    }
     conv_tc_kernel<BN, STAGES><<<grid, 128, smem, s>>>(*d, (const __half*)in, (const __half*)wgt, bias,
-                                                       (const __half*)residual, (__half*)out);
+                                                       (const __half*)residual, (__half*)out, g_ws, sps);
+    if (grid.z > 1) {
+        const size_t total = (size_t)M * d->cout;
+        const int blocks = (int)((total + 255) / 256 < (size_t)FM_NUM_SMS * 8 ? (total + 255) / 256 : FM_NUM_SMS * 8);
+        splitk_reduce_kernel<<<blocks, 256, 0, s>>>(*d, g_ws, (int)grid.z, bias, (const __half*)residual, (__half*)out);
+        fm_count_launches(1);
+    }
     return 0;
 }
 
 }  // namespace
+
+extern "C" int fm_conv_set_workspace(void* ws, long long bytes) {
+    g_ws = (float*)ws;
+    g_ws_bytes = bytes;
+    return FM_OK;
+}
 
 extern "C" int fm_conv2d_tc_supported(const FmConvDesc* d) {
     if (!d) return 0;
@@ -297,9 +374,20 @@ extern "C" int fm_conv2d_tc(const FmConvDesc* d, const void* in, const void* wgt
     FM_REQUIRE(d != nullptr, "fm_conv2d_tc: desc is NULL");
     FM_REQUIRE(fm_conv2d_tc_supported(d), "fm_conv2d_tc: shape not supported by the tcgen05 path");
     cudaStream_t s = (cudaStream_t)stream;
-    if (d->cout <= 32) launch_tc<32, 4>(d, in, wgt, bias, residual, out, s);
-    else if (d->cout <= 64) launch_tc<64, 4>(d, in, wgt, bias, residual, out, s);
-    else launch_tc<128, 3>(d, in, wgt, bias, residual, out, s);
+    const int nk = (d->kh * d->kw * d->cin + TC_BK - 1) / TC_BK;
+    // ring depth follows the K extent: short reductions (OSNet 1x1) want many co-resident CTAs, long ones (3x3 on
+    // wide layers) want many slices of copies in flight
+    if (d->cout <= 32) {
+        if (nk <= 2) launch_tc<32, 2>(d, in, wgt, bias, residual, out, s);
+        else launch_tc<32, 4>(d, in, wgt, bias, residual, out, s);
+    } else if (d->cout <= 64) {
+        if (nk <= 2) launch_tc<64, 2>(d, in, wgt, bias, residual, out, s);
+        else launch_tc<64, 4>(d, in, wgt, bias, residual, out, s);
+    } else {
+        if (nk <= 2) launch_tc<128, 2>(d, in, wgt, bias, residual, out, s);
+        else if (nk < 6) launch_tc<128, 3>(d, in, wgt, bias, residual, out, s);
+        else launch_tc<128, 6>(d, in, wgt, bias, residual, out, s);
+    }
     FM_CHECK_LAUNCH("fm_conv2d_tc");
     return FM_OK;
 }

@@ -38,16 +38,27 @@ __global__ void __launch_bounds__(32) nms_scan_blocked_kernel(const unsigned lon
             if (!((rem >> b) & 1ull)) { kept |= 1ull << b; rem |= row; }
         }
         if (lane == 0) keep[blk] = kept;
-        // survivors of this block suppress later blocks: independent loads, OR-reduced per word
-        for (int w = blk + 1 + lane; w < nw; w += 32) {
+        // survivors of this block suppress later blocks: lanes read consecutive words of a survivor's mask row
+        // (coalesced), four independent row loads in flight per step
+        for (int w0 = blk + 1; w0 < nw; w0 += 32) {
+            const int w = w0 + lane;
+            const bool wok = w < nw;
             unsigned long long acc = 0;
             unsigned long long k2 = kept;
             while (k2) {
-                const int b = __ffsll((long long)k2) - 1;
-                k2 &= k2 - 1;
-                acc |= mask[(size_t)(base + b) * mask_words + w];
+                int b[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    b[q] = k2 ? __ffsll((long long)k2) - 1 : -1;
+                    if (k2) k2 &= k2 - 1;
+                }
+                unsigned long long v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    v[q] = (b[q] >= 0 && wok) ? mask[(size_t)(base + b[q]) * mask_words + w] : 0ull;
+                acc |= (v[0] | v[1]) | (v[2] | v[3]);
             }
-            removed[w] |= acc;
+            if (wok) removed[w] |= acc;
         }
         __syncwarp();
     }

@@ -494,15 +494,14 @@ __device__ void jacobi_smallest_eigvec9(double* Amat /* 81, destroyed */, double
     const int n = 9;
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < n; ++j) Vmat[i * n + j] = (i == j) ? 1.0 : 0.0;
-    for (int sweep = 0; sweep < 60; ++sweep) {
-        double off = 0.0;
-        for (int i = 0; i < n; ++i)
-            for (int j = i + 1; j < n; ++j) off += Amat[i * n + j] * Amat[i * n + j];
-        if (off < 1e-300) break;
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        int rotated = 0;
         for (int p = 0; p < n; ++p)
             for (int q = p + 1; q < n; ++q) {
                 const double apq = Amat[p * n + q];
-                if (fabs(apq) < 1e-300) continue;
+                // off-diagonal already below double rounding of the diagonal pair: nothing left to annihilate
+                if (fabs(apq) <= 1e-17 * (fabs(Amat[p * n + p]) + fabs(Amat[q * n + q]))) continue;
+                ++rotated;
                 const double theta = (Amat[q * n + q] - Amat[p * n + p]) / (2.0 * apq);
                 const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
                 const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
@@ -522,6 +521,7 @@ __device__ void jacobi_smallest_eigvec9(double* Amat /* 81, destroyed */, double
                     Vmat[r * n + q] = s * vrp + c * vrq;
                 }
             }
+        if (!rotated) break;
     }
     int best = 0;
     for (int i = 1; i < n; ++i)

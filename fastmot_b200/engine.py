@@ -41,6 +41,17 @@ def _conv_desc(n, hi, wi, cin, cin_stride, cin_off, ho, wo, cout, cout_stride, c
     return d
 
 
+_WS = None
+
+
+def _ensure_workspace(lib, dev):
+    """fp32 split-K workspace of the tcgen05 conv (one per process; only the detector stream uses split-K)."""
+    global _WS
+    if _WS is None:
+        _WS = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+        lib.fm_conv_set_workspace(C.c_void_p(_WS.data_ptr()), _WS.numel())
+
+
 class _Net:
     """Shared plumbing: recorded launches, optional CUDA-graph replay, conv dispatch (tcgen05 when supported)."""
 
@@ -53,6 +64,7 @@ class _Net:
         self._keep = []
         self.n_tc = self.n_simt = 0
         self.dev = torch.device("cuda")
+        _ensure_workspace(self._lib, self.dev)
 
     def _conv(self, desc, x, w, b, out, residual=None):
         lib = self._lib

@@ -35,6 +35,8 @@ def _run_conv(fn_name, case, seed=0):
     from fastmot_b200.models.darknet import ACTS
     from oracle.nets import _act
     lib = _lib.load()
+    from fastmot_b200.engine import _ensure_workspace
+    _ensure_workspace(lib, torch.device("cuda"))     # enables the split-K path for small-M / large-K shapes
     n, h, w, cin, cout, k, stride, act, cis, cio, cos, coo, use_res = case
     g = torch.Generator().manual_seed(seed)
     pad = k // 2
@@ -79,6 +81,9 @@ def test_conv_simt_vs_torch(case):
     (1, 40, 40, 256, 512, 3, 2, 'leaky', 256, 0, 512, 0, False),
     (2, 16, 8, 96, 384, 1, 1, 'linear', 96, 0, 384, 0, True),
     (1, 13, 13, 512, 256, 1, 1, 'leaky', 1024, 512, 256, 0, False),
+    (1, 20, 20, 1024, 512, 3, 1, 'mish', 1024, 0, 512, 0, True),      # split-K with residual
+    (1, 40, 40, 256, 256, 3, 1, 'leaky', 256, 0, 512, 256, False),    # split-K into a concat slice
+    (1, 10, 10, 640, 24, 1, 1, 'logistic', 640, 0, 24, 0, False),     # split-K, ragged cout
 ])
 def test_conv_tc_vs_torch(case):
     r = _run_conv('fm_conv2d_tc', case)
