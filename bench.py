@@ -122,6 +122,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from fastmot_b200 import MOT, _lib
     from fastmot_b200 import engine as eng_mod
+    from fastmot_b200.utils import Profiler
     _lib.require_device()
     K, W = args.steps, args.warmup
     total = W + K
@@ -211,6 +212,9 @@ def run_ours(args):
                          "conv_ms_per_detector_frame": conv_ms / max(stage.get("detector_frames", 1), 1)},
             "stages_ms_per_step": {k: round(v / K, 4) for k, v in stage.items() if k.endswith("_ms")},
             "wall_ms_per_step": round(wall_dev * 1e3 / K, 4),
+            # reference stage names (mot.py:138-163), host wall clock per call over the whole run incl. warm-up
+            "stage_wall_ms_per_call": {k: round(Profiler.get_avg_millis(k), 3)
+                                       for k in ("track", "preproc", "detect", "extract", "assoc")},
         }
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(args.cpu_steps)

@@ -7,6 +7,9 @@
 #include "../../include/fastmot_b200.h"
 #include <float.h>
 
+int fm_launch_lsa_block(const double* cost, int nr, int nc, int* col4row, int* status, unsigned char* ws, int use_smem,
+                        size_t smem_bytes, cudaStream_t s);   // assoc_lsa_block.cu
+
 namespace {
 
 // ----------------------------------------------------------------------------------------------------------
@@ -449,8 +452,12 @@ extern "C" int fm_lsa(const double* cost, int nr, int nc, int* col4row, int* sta
     size_t bytes = lsa_bytes(a, b);
     int use_smem = bytes <= 46 * 1024;
     FM_REQUIRE(use_smem || workspace, "fm_lsa: workspace required for this size");
-    lsa_kernel<<<1, 32, use_smem ? bytes : 0, (cudaStream_t)stream>>>(cost, nr, nc, col4row, status,
-                                                                      (unsigned char*)workspace, use_smem);
+    if (b > 48)   // one thread per column: the per-step scan, resets and dual updates run CTA-wide
+        fm_launch_lsa_block(cost, nr, nc, col4row, status, (unsigned char*)workspace, use_smem, bytes,
+                            (cudaStream_t)stream);
+    else
+        lsa_kernel<<<1, 32, use_smem ? bytes : 0, (cudaStream_t)stream>>>(cost, nr, nc, col4row, status,
+                                                                          (unsigned char*)workspace, use_smem);
     FM_CHECK_LAUNCH("fm_lsa");
     return FM_OK;
 }

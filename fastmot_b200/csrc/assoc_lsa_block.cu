@@ -1,0 +1,152 @@
+// Rectangular LSA with a whole CTA (one thread per remaining column): same replay of SciPy's
+// shortest-augmenting-path solver as lsa_kernel in assoc.cu (scan order of `remaining`, swap-with-last compaction,
+// "last unassigned among equal minima, else first minimum", fp64 operation order), but the per-step scan, the dual
+// update and the resets run across up to 1024 threads instead of one warp.  Bit-exact by construction: every
+// floating-point expression is evaluated by exactly one thread in SciPy's order; only the (associative) min / index
+// selection is parallel.
+#include "common.cuh"
+#include "../../include/fastmot_b200.h"
+
+namespace {
+
+struct Bufs {
+    double *u, *v, *spc;
+    int *path, *col4row, *row4col, *remaining;
+    unsigned char *SR, *SC;
+};
+
+__device__ __forceinline__ Bufs carve(unsigned char* base, int nr, int nc) {
+    Bufs b;
+    size_t off = 0;
+    b.u = (double*)(base + off); off += sizeof(double) * nr;
+    b.v = (double*)(base + off); off += sizeof(double) * nc;
+    b.spc = (double*)(base + off); off += sizeof(double) * nc;
+    b.path = (int*)(base + off); off += sizeof(int) * nc;
+    b.col4row = (int*)(base + off); off += sizeof(int) * nr;
+    b.row4col = (int*)(base + off); off += sizeof(int) * nc;
+    b.remaining = (int*)(base + off); off += sizeof(int) * nc;
+    b.SR = base + off; off += nr;
+    b.SC = base + off;
+    return b;
+}
+
+__global__ void __launch_bounds__(1024) lsa_block_kernel(const double* __restrict__ cost, int nr0, int nc0,
+                                                          int* __restrict__ out_col4row, int* __restrict__ status,
+                                                          unsigned char* gws, int use_smem) {
+    extern __shared__ __align__(16) unsigned char s_ws[];
+    __shared__ double s_wmin[32];
+    __shared__ int s_wfirst[32], s_wlast[32];
+    __shared__ double s_minval;
+    __shared__ int s_i, s_sink, s_numrem, s_infeasible;
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarps = T >> 5;
+    const bool transpose = nc0 < nr0;
+    const int nr = transpose ? nc0 : nr0;
+    const int nc = transpose ? nr0 : nc0;
+    Bufs B = carve(use_smem ? s_ws : gws, nr, nc);
+#define COST(i, j) (transpose ? cost[(size_t)(j) * nc0 + (i)] : cost[(size_t)(i) * nc0 + (j)])
+    for (int k = tid; k < nr; k += T) { B.u[k] = 0.0; B.col4row[k] = -1; }
+    for (int k = tid; k < nc; k += T) { B.v[k] = 0.0; B.row4col[k] = -1; B.path[k] = -1; }
+    if (tid == 0) { status[0] = 0; s_infeasible = 0; }
+    __syncthreads();
+    for (int curRow = 0; curRow < nr; ++curRow) {
+        for (int k = tid; k < nc; k += T) { B.remaining[k] = nc - k - 1; B.SC[k] = 0; B.spc[k] = INFINITY; }
+        for (int k = tid; k < nr; k += T) B.SR[k] = 0;
+        if (tid == 0) { s_minval = 0.0; s_i = curRow; s_sink = -1; s_numrem = nc; }
+        __syncthreads();
+        while (true) {
+            const int i = s_i;
+            const int num_remaining = s_numrem;
+            const double minVal = s_minval;
+            const double ui = B.u[i];
+            double l_min = INFINITY;
+            int l_first = 0x7fffffff, l_lastU = -1;
+            for (int it = tid; it < num_remaining; it += T) {
+                const int j = B.remaining[it];
+                const double r = __dsub_rn(__dsub_rn(__dadd_rn(minVal, COST(i, j)), ui), B.v[j]);
+                double s = B.spc[j];
+                if (r < s) { B.path[j] = i; B.spc[j] = r; s = r; }
+                const bool un = B.row4col[j] == -1;
+                if (s < l_min) { l_min = s; l_first = it; l_lastU = un ? it : -1; }
+                else if (s == l_min) { if (l_first == 0x7fffffff) l_first = it; if (un) l_lastU = it; }
+            }
+            // warp level
+            double m = l_min;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+            int cf = (l_min == m) ? l_first : 0x7fffffff;
+            int cl = (l_min == m) ? l_lastU : -1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                cf = min(cf, __shfl_xor_sync(0xffffffffu, cf, o));
+                cl = max(cl, __shfl_xor_sync(0xffffffffu, cl, o));
+            }
+            if (lane == 0) { s_wmin[wid] = m; s_wfirst[wid] = cf; s_wlast[wid] = cl; }
+            __syncthreads();
+            if (tid == 0) {
+                if (i == curRow || true) B.SR[i] = 1;
+                double gm = INFINITY;
+                for (int w = 0; w < nwarps; ++w) gm = fmin(gm, s_wmin[w]);
+                int gf = 0x7fffffff, gl = -1;
+                for (int w = 0; w < nwarps; ++w)
+                    if (s_wmin[w] == gm) { gf = min(gf, s_wfirst[w]); gl = max(gl, s_wlast[w]); }
+                if (gm == INFINITY) {
+                    s_infeasible = 1;
+                } else {
+                    s_minval = gm;
+                    const int index = (gl >= 0) ? gl : gf;
+                    const int j = B.remaining[index];
+                    const int r4c = B.row4col[j];
+                    if (r4c == -1) s_sink = j; else s_i = r4c;
+                    B.SC[j] = 1;
+                    B.remaining[index] = B.remaining[num_remaining - 1];
+                    s_numrem = num_remaining - 1;
+                }
+            }
+            __syncthreads();
+            if (s_infeasible || s_sink != -1) break;
+        }
+        if (s_infeasible) break;
+        const double minVal = s_minval;
+        const int sink = s_sink;
+        if (tid == 0) B.u[curRow] = __dadd_rn(B.u[curRow], minVal);
+        for (int k = tid; k < nr; k += T)
+            if (B.SR[k] && k != curRow) B.u[k] = __dadd_rn(B.u[k], __dsub_rn(minVal, B.spc[B.col4row[k]]));
+        for (int k = tid; k < nc; k += T)
+            if (B.SC[k]) B.v[k] = __dsub_rn(B.v[k], __dsub_rn(minVal, B.spc[k]));
+        __syncthreads();
+        if (tid == 0) {
+            int j = sink;
+            while (true) {
+                const int ii = B.path[j];
+                B.row4col[j] = ii;
+                const int tmp = B.col4row[ii];
+                B.col4row[ii] = j;
+                j = tmp;
+                if (ii == curRow) break;
+            }
+        }
+        __syncthreads();
+    }
+    if (s_infeasible) {
+        if (tid == 0) status[0] = 1;
+        for (int k = tid; k < nr0; k += T) out_col4row[k] = -1;
+        return;
+    }
+    for (int k = tid; k < nr0; k += T) {
+        int c = transpose ? B.row4col[k] : B.col4row[k];
+        if (c >= 0 && cost[(size_t)k * nc0 + c] >= FM_INF_COST) c = -2 - c;
+        out_col4row[k] = c;
+    }
+#undef COST
+}
+
+}  // namespace
+
+int fm_launch_lsa_block(const double* cost, int nr, int nc, int* col4row, int* status, unsigned char* ws, int use_smem,
+                        size_t smem_bytes, cudaStream_t s) {
+    const int big = nr > nc ? nr : nc;
+    int threads = 64;
+    while (threads < big && threads < 1024) threads <<= 1;
+    lsa_block_kernel<<<1, threads, use_smem ? smem_bytes : 0, s>>>(cost, nr, nc, col4row, status, ws, use_smem);
+    return 0;
+}
