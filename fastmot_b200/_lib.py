@@ -94,6 +94,7 @@ SIGNATURES = {
     "fm_global_avgpool": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p]),
     "fm_channel_gate": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "fm_fc_norm": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "fm_channel_gate4": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
     "fm_nms_mask_bytes": (c_ll, [c_i]),
     "fm_diou_nms_filter": (c_i, [c_p, c_p, c_p, c_i, c_d, c_d, c_d, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
 }

@@ -241,6 +241,8 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
     const int m = m0 + tid;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     const bool vec_ok = ((d.cout_stride | d.cout_offset) & 7) == 0;
+    const int act = d.act & 0xff;
+    const bool res_first = (d.act & FM_ACT_AFTER_RESIDUAL) != 0;   // act(conv + residual) instead of act(conv) + residual
     const bool res_vec = residual != nullptr && ((d.res_stride | d.res_offset) & 7) == 0;
 #pragma unroll 1
     for (int j0 = 0; j0 < BN; j0 += 32) {
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 float x = v[q] + ((bias && n + q < d.cout) ? bias[n + q] : 0.f);
-                v[q] = tc_act(x, d.act);
+                v[q] = res_first ? x : tc_act(x, act);
             }
             __half* op = out + (size_t)m * d.cout_stride + d.cout_offset + n;
             if (n + 8 <= d.cout && vec_ok) {
@@ -280,13 +282,13 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
                 }
                 __align__(16) __half h[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) h[q] = __float2half(v[q]);
+                for (int q = 0; q < 8; ++q) h[q] = __float2half(res_first ? tc_act(v[q], act) : v[q]);
                 *(int4*)op = *(const int4*)h;
             } else {
                 for (int q = 0; q < 8 && n + q < d.cout; ++q) {
                     float x = v[q];
                     if (residual) x += __half2float(residual[(size_t)m * d.res_stride + d.res_offset + n + q]);
-                    op[q] = __float2half(x);
+                    op[q] = __float2half(res_first ? tc_act(x, act) : x);
                 }
             }
         }
@@ -309,8 +311,12 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(FmConvDesc d, const 
         const int n = (int)(i - m * d.cout);
         float acc = 0.f;
         for (int z = 0; z < splits; ++z) acc += ws[(size_t)z * total + i];
-        float v = tc_act(acc + (bias ? bias[n] : 0.f), d.act);
+        const int act = d.act & 0xff;
+        const bool res_first = (d.act & FM_ACT_AFTER_RESIDUAL) != 0;
+        float v = acc + (bias ? bias[n] : 0.f);
+        if (!res_first) v = tc_act(v, act);
         if (residual) v += __half2float(residual[m * d.res_stride + d.res_offset + n]);
+        if (res_first) v = tc_act(v, act);
         out[m * d.cout_stride + d.cout_offset + n] = __float2half(v);
     }
 }

@@ -104,8 +104,10 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(FmConvDesc d, const __ha
             const int n = n0 + tx * 4 + j;
             if (n >= d.cout) continue;
             float v = acc[i][j] + (bias ? bias[n] : 0.f);
-            v = apply_act(v, d.act);
+            const bool res_first = (d.act & FM_ACT_AFTER_RESIDUAL) != 0;
+            if (!res_first) v = apply_act(v, d.act & 0xff);
             if (residual) v += __half2float(residual[(size_t)m * d.res_stride + d.res_offset + n]);
+            if (res_first) v = apply_act(v, d.act & 0xff);
             out[(size_t)m * d.cout_stride + d.cout_offset + n] = __float2half(v);
         }
     }

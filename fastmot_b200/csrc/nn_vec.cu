@@ -333,3 +333,108 @@ int fm_vec_gate_apply(const void* x, const float* gate, void* acc, size_t per_sa
                                                      accumulate);
     return 1;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// OSNet unified aggregation gate for the four streams of a block (shared gate weights):
+//   acc = sum_s x_s * sigmoid(W2 relu(W1 GAP(x_s) + b1) + b2)
+// three launches (pool all streams, tiny FCs, one fused apply) instead of 4 x (pool, FC, read-modify-write).
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Ptr4 { const __half* p[4]; };
+
+__global__ void __launch_bounds__(256) gap4_vec(Ptr4 x, float* __restrict__ pooled /* [4][n][c] */, int n, int hw, int c) {
+    __shared__ float s_acc[32][65];
+    const int b = blockIdx.x, slab = blockIdx.y, st = blockIdx.z;
+    const int c0 = slab * 64;
+    const int cgs = min(64, c - c0) >> 3;
+    const int tid = threadIdx.x, g = tid % 8, prow = tid / 8;
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    if (g < cgs) {
+        const __half* p = x.p[st] + (size_t)b * hw * c + c0 + g * 8;
+        for (int i = prow; i < hw; i += 32) {
+            float a[8];
+            to_f(ld8(p + (size_t)i * c), a);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] += a[q];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s_acc[prow][g * 8 + q] = acc[q];
+    __syncthreads();
+    if (tid < 64 && c0 + tid < c) {
+        float a = 0.f;
+        for (int r = 0; r < 32; ++r) a += s_acc[r][tid];
+        pooled[((size_t)st * n + b) * c + c0 + tid] = a / hw;
+    }
+}
+
+__global__ void __launch_bounds__(128) gate_fc4_kernel(const float* __restrict__ pooled, const float* __restrict__ w1,
+                                                        const float* __restrict__ b1, const float* __restrict__ w2,
+                                                        const float* __restrict__ b2, float* __restrict__ gate, int c,
+                                                        int cr) {
+    extern __shared__ float sh[];
+    float* sp = sh;
+    float* sh1 = sh + c;
+    const size_t row = blockIdx.x;          // st * n + b
+    for (int i = threadIdx.x; i < c; i += blockDim.x) sp[i] = pooled[row * c + i];
+    __syncthreads();
+    for (int j = threadIdx.x; j < cr; j += blockDim.x) {
+        float a = b1[j];
+        for (int i = 0; i < c; ++i) a += w1[(size_t)j * c + i] * sp[i];
+        sh1[j] = a > 0.f ? a : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+        float a = b2[i];
+        for (int j = 0; j < cr; ++j) a += w2[(size_t)i * cr + j] * sh1[j];
+        gate[row * c + i] = 1.f / (1.f + __expf(-a));
+    }
+}
+
+__global__ void __launch_bounds__(256) gate_apply4_vec(Ptr4 x, const float* __restrict__ gate /* [4][n][c] */,
+                                                        __half* __restrict__ acc, size_t per_sample, int n, int c,
+                                                        size_t total8) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t e = i * 8;
+        const int ch = e % c;
+        const size_t b = e / per_sample;
+        float out[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) out[q] = 0.f;
+#pragma unroll
+        for (int st = 0; st < 4; ++st) {
+            float v[8];
+            to_f(ld8(x.p[st] + e), v);
+            const float* gp = gate + ((size_t)st * n + b) * c + ch;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) out[q] += v[q] * gp[q];
+        }
+        st8(acc + e, to_h(out));
+    }
+}
+
+}  // namespace
+
+extern "C" int fm_channel_gate4(const void* x0, const void* x1, const void* x2, const void* x3, float* pooled,
+                                float* gate, const float* w1, const float* b1, const float* w2, const float* b2,
+                                void* acc, int n, int hw, int c, int cr, void* stream) {
+    if (n <= 0) return FM_OK;
+    if (c & 7) {
+        fm_set_last_error("fm_channel_gate4: channel count must be a multiple of 8");
+        return FM_ERR_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    Ptr4 p;
+    p.p[0] = (const __half*)x0; p.p[1] = (const __half*)x1; p.p[2] = (const __half*)x2; p.p[3] = (const __half*)x3;
+    dim3 g1(n, (c + 63) / 64, 4);
+    gap4_vec<<<g1, 256, 0, s>>>(p, pooled, n, hw, c);
+    gate_fc4_kernel<<<4 * n, 128, (c + cr) * sizeof(float), s>>>(pooled, w1, b1, w2, b2, gate, c, cr);
+    const size_t total = (size_t)n * hw * c;
+    gate_apply4_vec<<<vgrid(total >> 3), 256, 0, s>>>(p, gate, (__half*)acc, (size_t)hw * c, n, c, total >> 3);
+    fm_count_launches(2);
+    FM_CHECK_LAUNCH("fm_channel_gate4");
+    return FM_OK;
+}

@@ -15,6 +15,7 @@ from .devmem import ptr, stream_ptr
 from .models import darknet, osnet
 
 _ACT = darknet.ACTS
+ACT_AFTER_RESIDUAL = 0x100
 IN_C_PAD = 8      # network inputs are NHWC with 3 real + 5 zero channels: one 16-byte chunk per pixel
 
 
@@ -268,9 +269,10 @@ class OSNetEngine(_Net):
                 params[name] = tuple(torch.as_tensor(a).to(dev) for a in self.weights[name])
             return params[name]
 
-        self.pooled = torch.zeros(B, 512, dtype=torch.float32, device=dev)
-        self.gate_tmp = torch.zeros(B, 512, dtype=torch.float32, device=dev)
+        self.pooled = torch.zeros(4 * B, 512, dtype=torch.float32, device=dev)
+        self.gate_tmp = torch.zeros(4 * B, 512, dtype=torch.float32, device=dev)
         self._params = params
+        fused_add = {}
         for k, op in enumerate(self.ops):
             kind = op[0]
             if kind == 'conv':
@@ -284,9 +286,19 @@ class OSNetEngine(_Net):
                 bd = torch.as_tensor(bs).to(dev).float().contiguous()
                 params[name] = (wd, bd)
                 y = alloc(B * ho * wo * cout)
-                d = _conv_desc(B, h, w, xc, xc, 0, ho, wo, cout, cout, 0, ks, stride, pad, _ACT[act])
-                self._conv(d, x, wd, bd, y)
-                new = (dst, (y, cout, ho, wo))
+                nxt = self.ops[k + 1] if k + 1 < len(self.ops) else None
+                if nxt is not None and nxt[0] == 'add_relu' and nxt[1] == dst and act == 'linear' and nxt[2] in live:
+                    # relu(conv3(x) + identity): residual + activation in the conv epilogue, no extra pass
+                    d = _conv_desc(B, h, w, xc, xc, 0, ho, wo, cout, cout, 0, ks, stride, pad,
+                                   _ACT['relu'] | ACT_AFTER_RESIDUAL)
+                    d.res_stride, d.res_offset = cout, 0
+                    self._conv(d, x, wd, bd, y, residual=live[nxt[2]][0])
+                    fused_add[k + 1] = nxt[2]
+                    new = (nxt[3], (y, cout, ho, wo))
+                else:
+                    d = _conv_desc(B, h, w, xc, xc, 0, ho, wo, cout, cout, 0, ks, stride, pad, _ACT[act])
+                    self._conv(d, x, wd, bd, y)
+                    new = (dst, (y, cout, ho, wo))
             elif kind == 'dw':
                 _, name, c, act, src, dst = op
                 x, xc, h, w = live[src]
@@ -317,7 +329,18 @@ class OSNetEngine(_Net):
                 self._add('fm_channel_gate', ptr(x), ptr(self.pooled), ptr(self.gate_tmp), ptr(w1), ptr(b1), ptr(w2),
                           ptr(b2), ptr(a), B, h * w, c, w1.shape[0], accumulate)
                 new = None
+            elif kind == 'gate4':
+                _, name, c, srcs, acc = op
+                xs = [live[s_][0] for s_ in srcs]
+                _, xc, h, w = live[srcs[0]]
+                w1, b1, w2, b2 = dparam(name)
+                a = alloc(B * h * w * c)
+                self._add('fm_channel_gate4', ptr(xs[0]), ptr(xs[1]), ptr(xs[2]), ptr(xs[3]), ptr(self.pooled),
+                          ptr(self.gate_tmp), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(a), B, h * w, c, w1.shape[0])
+                new = (acc, (a, c, h, w))
             elif kind == 'add_relu':
+                if k in fused_add:        # folded into the preceding conv's epilogue
+                    continue
                 a, ac, h, w = live[op[1]]
                 b = live[op[2]][0]
                 y = alloc(B * h * w * ac)
@@ -355,6 +378,8 @@ class OSNetEngine(_Net):
             return [op[1]]
         if kind == 'gate':
             return [op[3], op[4]]
+        if kind == 'gate4':
+            return list(op[3])
         if kind == 'add_relu':
             return [op[1], op[2]]
         if kind == 'fc':

@@ -117,6 +117,15 @@ def calibrate_osnet(ops, weights, hw=(256, 128), seed=78):
                 gt = torch.sigmoid(F.relu(xx.mean((2, 3)) @ w1.T + b1) @ w2.T + b2)
                 y = xx * gt[:, :, None, None]
                 bufs[acc] = y + bufs[acc] if accumulate else y
+            elif kind == 'gate4':
+                _, name, c, srcs, acc = op
+                w1, b1, w2, b2 = (torch.as_tensor(a) for a in weights[name])
+                tot = 0
+                for s_ in srcs:
+                    xx = bufs[s_]
+                    gt = torch.sigmoid(F.relu(xx.mean((2, 3)) @ w1.T + b1) @ w2.T + b2)
+                    tot = tot + xx * gt[:, :, None, None]
+                bufs[acc] = tot
             elif kind == 'add_relu':
                 bufs[op[3]] = F.relu(bufs[op[1]] + bufs[op[2]])
             elif kind == 'gap':

@@ -11,6 +11,7 @@ Op tuples (executed by fastmot_b200.engine.OSNetEngine and, in fp32 torch, by or
   ('dw',   name, c, act, src, dst)                              depthwise 3x3 s1 p1, weights[name] = (w[9][c], b)
   ('maxpool3s2', src, dst) / ('avgpool2', src, dst)
   ('gate', name, c, src, acc, accumulate)                       acc (+)= src * sigmoid(fc2(relu(fc1(gap(src)))))
+  ('gate4', name, c, (s0, s1, s2, s3), acc)                    acc = sum_i s_i * gate(s_i), shared gate weights
   ('add_relu', a, b, dst)
   ('gap', src, dst) / ('fc', name, cin, cout, src, dst)
 `src`/`dst` are symbolic buffer names.
@@ -35,6 +36,7 @@ def build_osnet(width=1.0, feature_dim=512):
         x1 = buf('t')
         ops.append(('conv', f'{name}.conv1', cin, mid, 1, 1, 0, 'relu', src, x1))
         acc = buf('t')
+        tails = []
         for s in range(4):
             prev = x1
             for j in range(s + 1):
@@ -42,15 +44,17 @@ def build_osnet(width=1.0, feature_dim=512):
                 ops.append(('conv', f'{name}.conv2{"abcd"[s]}.{j}.pw', mid, mid, 1, 1, 0, 'linear', prev, a))
                 ops.append(('dw', f'{name}.conv2{"abcd"[s]}.{j}.dw', mid, 'relu', a, b2))
                 prev = b2
-            ops.append(('gate', f'{name}.gate', mid, prev, acc, 1 if s else 0))
-        x3 = buf('t')
-        ops.append(('conv', f'{name}.conv3', mid, cout, 1, 1, 0, 'linear', acc, x3))
+            tails.append(prev)
+        # the four streams share one gate module; acc = sum_s gate(x_s) * x_s in a single pass
+        ops.append(('gate4', f'{name}.gate', mid, tuple(tails), acc))
         ident = src
         if cin != cout:
             ident = buf('t')
             ops.append(('conv', f'{name}.downsample', cin, cout, 1, 1, 0, 'linear', src, ident))
+        x3 = buf('t')
+        ops.append(('conv', f'{name}.conv3', mid, cout, 1, 1, 0, 'linear', acc, x3))
         out = buf('t')
-        ops.append(('add_relu', x3, ident, out))
+        ops.append(('add_relu', x3, ident, out))      # the engine fuses this into conv3's epilogue
         return out
 
     for stage in range(3):
@@ -86,7 +90,7 @@ def synthetic_weights(ops, seed_base=5000, reduction=16, calibrate=True):
             rng = np.random.default_rng(seed_base + k)
             w[name] = (rng.normal(0, np.sqrt(2.0 / 9), (9, c)).astype(np.float32),
                        rng.normal(0, 0.02, c).astype(np.float32))
-        elif kind == 'gate':
+        elif kind in ('gate', 'gate4'):
             _, name, c = op[:3]
             if name not in w:
                 rng = np.random.default_rng(seed_base + k)
@@ -131,6 +135,8 @@ def count_macs(ops, h=256, w=128):
             shapes[op[2]] = (hh // 2, ww // 2)
         elif kind == 'gate':
             shapes.setdefault(op[4], shapes[op[3]])
+        elif kind == 'gate4':
+            shapes[op[4]] = shapes[op[3][0]]
         elif kind == 'add_relu':
             shapes[op[3]] = shapes[op[1]]
         elif kind == 'fc':

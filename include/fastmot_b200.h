@@ -175,6 +175,8 @@ int fm_diou_nms_filter(unsigned long long* keys, const float* dense, const int* 
 #define FM_ACT_SWISH 3
 #define FM_ACT_LOGISTIC 4
 #define FM_ACT_RELU 5
+#define FM_ACT_AFTER_RESIDUAL 0x100 /* OR-ed into `act`: out = act(conv + bias + residual) (OSNet block tail) instead of
+                                       act(conv + bias) + residual (Darknet shortcut after a conv) */
 
 typedef struct FmConvDesc {
     int n, hi, wi, cin, cin_stride, cin_offset;     /* input  [n][hi][wi][cin_stride], channels [off, off+cin) */
@@ -210,6 +212,11 @@ int fm_global_avgpool(const void* in, float* out, int n, int hw, int c, void* st
 /* OSNet channel gate: acc (+)= x * sigmoid(W2 relu(W1 GAP(x) + b1) + b2) */
 int fm_channel_gate(const void* x, float* pooled, float* gate, const float* w1, const float* b1, const float* w2,
                     const float* b2, void* acc, int n, int hw, int c, int cr, int accumulate, void* stream);
+/* The four streams of an OSBlock share one gate: acc = sum_s x_s * gate(x_s) in one fused pass.
+ * pooled / gate: scratch of 4*n*c floats each. */
+int fm_channel_gate4(const void* x0, const void* x1, const void* x2, const void* x3, float* pooled, float* gate,
+                     const float* w1, const float* b1, const float* w2, const float* b2, void* acc, int n, int hw, int c,
+                     int cr, void* stream);
 /* FC (+ReLU) and the row L2 normalisation of FeatureExtractor.postprocess (feature_extractor.py:73). */
 int fm_fc_norm(const float* in, const float* w, const float* bias, float* out, int n, int cin, int cout, int relu,
                int normalize, void* stream);

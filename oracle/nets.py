@@ -98,6 +98,15 @@ def run_osnet(ops, weights, x, quantize=None):
             g = torch.sigmoid(F.relu(p @ w1.T + b1) @ w2.T + b2)
             y = xx * g[:, :, None, None]
             bufs[acc] = q(y + bufs[acc]) if accumulate else q(y)
+        elif kind == 'gate4':
+            _, name, c, srcs, acc = op
+            w1, b1, w2, b2 = (torch.as_tensor(a) for a in weights[name])
+            tot = 0
+            for s_ in srcs:
+                xx = bufs[s_]
+                g = torch.sigmoid(F.relu(xx.mean((2, 3)) @ w1.T + b1) @ w2.T + b2)
+                tot = tot + xx * g[:, :, None, None]
+            bufs[acc] = q(tot)
         elif kind == 'add_relu':
             bufs[op[3]] = q(F.relu(bufs[op[1]] + bufs[op[2]]))
         elif kind == 'gap':
