@@ -110,6 +110,18 @@ def det_override(scene):
     return f
 
 
+def reduce_max_ms(ms, world, device):
+    """Timing of a multi-rank run = max over ranks (one all_reduce on the given device; NCCL on GPUs, gloo in the
+    CPU test)."""
+    if world <= 1:
+        return float(ms)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(ms)], device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 # ------------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -154,11 +166,7 @@ def run_ours(args):
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = reduce_max_ms(e0.elapsed_time(e1), world, dev)
         return ms, wall, n_vis
 
     # ---- pass 1: frames resident in HBM ----

@@ -300,6 +300,202 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
                      "r"((uint32_t)(BN < 32 ? 32 : BN)));
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Small-K variant (K <= 128: the 1x1 convs of OSNet, M up to 460 k pixels): memory/latency bound, so each CTA keeps
+// the whole weight matrix resident in smem, walks many 128-pixel tiles, double-buffers the A tile (cp.async for
+// tile t+1 is in flight while tile t is multiplied and written out) and double-buffers the accumulator in TMEM.
+// TMEM alloc / barrier init / weight loads are paid once per CTA instead of once per tile.
+// ---------------------------------------------------------------------------------------------------------
+template <int BN, int NK>
+__global__ void __launch_bounds__(128) conv_tc_smallk_kernel(FmConvDesc d, const __half* __restrict__ in,
+                                                              const __half* __restrict__ wgt,
+                                                              const float* __restrict__ bias,
+                                                              const __half* __restrict__ residual,
+                                                              __half* __restrict__ out, int m_tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int A_BYTES = TC_BM * 128, B_BYTES = BN * 128;
+    uint8_t* sB = smem;                                  // NK slices of B
+    uint8_t* sA0 = smem + NK * B_BYTES;                  // 2 x NK slices of A
+    __shared__ uint64_t bar_mma[2];
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int n0 = blockIdx.y * BN;
+    const int M = d.n * d.ho * d.wo;
+    const int Ktot = d.kh * d.kw * d.cin;
+    if (tid == 0) {
+        mbar_init(&bar_mma[0], 1);
+        mbar_init(&bar_mma[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "r"((uint32_t)(2 * BN < 32 ? 32 : 2 * BN)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem;
+    const int c = tid & 7, rbase = tid >> 3;
+    const uint32_t idesc = make_idesc(BN);
+
+    auto load_A = [&](int tile, int buf) {
+        const int m0 = tile * TC_BM;
+#pragma unroll
+        for (int ks = 0; ks < NK; ++ks) {
+            uint8_t* sA = sA0 + (size_t)(buf * NK + ks) * A_BYTES;
+            const int kelem = ks * TC_BK + c * 8;
+            const bool kvalid = kelem < Ktot;
+            const int tap = kvalid ? kelem / d.cin : 0;
+            const int cch = kvalid ? kelem - tap * d.cin : 0;
+            const int fr = tap / d.kw, fs = tap - fr * d.kw;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = rbase + 16 * i;
+                const int m = m0 + r;
+                const __half* src = in;
+                uint32_t bytes = 0;
+                if (kvalid && m < M) {
+                    const int wo = m % d.wo, t = m / d.wo, ho = t % d.ho, nb = t / d.ho;
+                    const int hi = ho * d.stride - d.pad + fr, wi = wo * d.stride - d.pad + fs;
+                    if (hi >= 0 && hi < d.hi && wi >= 0 && wi < d.wi) {
+                        src = in + (((size_t)nb * d.hi + hi) * d.wi + wi) * d.cin_stride + d.cin_offset + cch;
+                        bytes = 16;
+                    }
+                }
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
+                                 smem_u32(sA + r * 128 + ((c ^ (r & 7)) << 4))),
+                             "l"(src), "r"(bytes));
+            }
+        }
+    };
+    // weights: resident for the whole CTA
+#pragma unroll
+    for (int ks = 0; ks < NK; ++ks) {
+        const int kelem = ks * TC_BK + c * 8;
+#pragma unroll
+        for (int i = 0; i < BN / 16; ++i) {
+            const int r = rbase + 16 * i;
+            const int n = n0 + r;
+            const bool ok = kelem < Ktot && n < d.cout;
+            const __half* src = ok ? wgt + (size_t)n * Ktot + kelem : wgt;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
+                             smem_u32(sB + (size_t)ks * B_BYTES + r * 128 + ((c ^ (r & 7)) << 4))),
+                         "l"(src), "r"(ok ? 16u : 0u));
+        }
+    }
+    int tile = blockIdx.x;
+    if (tile < m_tiles) load_A(tile, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const bool vec_ok = ((d.cout_stride | d.cout_offset) & 7) == 0;
+    const bool res_vec = residual != nullptr && ((d.res_stride | d.res_offset) & 7) == 0;
+    const int act = d.act & 0xff;
+    const bool res_first = (d.act & FM_ACT_AFTER_RESIDUAL) != 0;
+    int it = 0;
+    for (; tile < m_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int next = tile + gridDim.x;
+        if (next < m_tiles) load_A(next, buf ^ 1);     // buffer buf^1 was consumed by the MMAs of iteration it-1,
+        asm volatile("cp.async.commit_group;" ::: "memory");   // whose completion we waited for in that epilogue
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < NK; ++ks) {
+                const uint32_t a_addr = smem_u32(sA0 + (size_t)(buf * NK + ks) * A_BYTES);
+                const uint32_t b_addr = smem_u32(sB + (size_t)ks * B_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k)
+                    mma_f16(tmem_base + buf * BN, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32),
+                            idesc, (ks > 0 || k > 0) ? 1u : 0u);
+            }
+            tc_commit(&bar_mma[buf]);
+        }
+        mbar_wait(&bar_mma[buf], (uint32_t)((it >> 1) & 1));
+        tc_fence_after();
+        // ---- epilogue of this tile (the next tile's copies are already in flight) ----
+        const int m = tile * TC_BM + tid;
+        const uint32_t lane_addr = tmem_base + buf * BN + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int j0 = 0; j0 < BN; j0 += 32) {
+            float v32[32];
+            tmem_ld32(lane_addr + j0, v32);
+            if (m >= M) continue;
+#pragma unroll
+            for (int jj = 0; jj < 32; jj += 8) {
+                const int n = n0 + j0 + jj;
+                if (n >= d.cout) break;
+                float* v = v32 + jj;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float x = v[q] + ((bias && n + q < d.cout) ? bias[n + q] : 0.f);
+                    v[q] = res_first ? x : tc_act(x, act);
+                }
+                __half* op = out + (size_t)m * d.cout_stride + d.cout_offset + n;
+                if (n + 8 <= d.cout && vec_ok) {
+                    if (residual) {
+                        const __half* rp = residual + (size_t)m * d.res_stride + d.res_offset + n;
+                        if (res_vec) {
+                            const int4 rv = *(const int4*)rp;
+                            const __half* rh = (const __half*)&rv;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) v[q] += __half2float(rh[q]);
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) v[q] += __half2float(rp[q]);
+                        }
+                    }
+                    __align__(16) __half h[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) h[q] = __float2half(res_first ? tc_act(v[q], act) : v[q]);
+                    *(int4*)op = *(const int4*)h;
+                } else {
+                    for (int q = 0; q < 8 && n + q < d.cout; ++q) {
+                        float x = v[q];
+                        if (residual) x += __half2float(residual[(size_t)m * d.res_stride + d.res_offset + n + q]);
+                        op[q] = __float2half(res_first ? tc_act(x, act) : x);
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();      // all TMEM reads of accumulator `buf` done before it is overwritten two tiles later
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"((uint32_t)(2 * BN < 32 ? 32 : 2 * BN)));
+}
+
+template <int BN, int NK>
+int launch_tc_smallk(const FmConvDesc* d, const void* in, const void* wgt, const float* bias, const void* residual,
+                     void* out, cudaStream_t s) {
+    constexpr int smem = NK * BN * 128 + 2 * NK * TC_BM * 128 + 1024;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(conv_tc_smallk_kernel<BN, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr = true;
+    }
+    const int M = d->n * d->ho * d->wo;
+    const int m_tiles = fm_cdiv(M, TC_BM);
+    const int n_tiles = fm_cdiv(d->cout, BN);
+    int per_sm = (220 * 1024) / smem;                 // shared-memory limit
+    if (per_sm > 512 / (2 * BN)) per_sm = 512 / (2 * BN);   // TMEM limit: two BN-column accumulators per CTA
+    if (per_sm > 4) per_sm = 4;
+    int gx = FM_NUM_SMS * per_sm / n_tiles;
+    if (gx < 1) gx = 1;
+    if (gx > m_tiles) gx = m_tiles;
+    dim3 grid(gx, n_tiles, 1);
+    conv_tc_smallk_kernel<BN, NK><<<grid, 128, smem, s>>>(*d, (const __half*)in, (const __half*)wgt, bias,
+                                                          (const __half*)residual, (__half*)out, m_tiles);
+    return 0;
+}
+
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(FmConvDesc d, const float* __restrict__ ws, int splits,
                                                              const float* __restrict__ bias,
                                                              const __half* __restrict__ residual,
@@ -381,6 +577,14 @@ extern "C" int fm_conv2d_tc(const FmConvDesc* d, const void* in, const void* wgt
     FM_REQUIRE(fm_conv2d_tc_supported(d), "fm_conv2d_tc: shape not supported by the tcgen05 path");
     cudaStream_t s = (cudaStream_t)stream;
     const int nk = (d->kh * d->kw * d->cin + TC_BK - 1) / TC_BK;
+    const int m_tiles_all = (d->n * d->ho * d->wo + TC_BM - 1) / TC_BM;
+    if (nk <= 2 && m_tiles_all >= 2 * FM_NUM_SMS) {      // big-M, tiny-K: persistent double-buffered variant
+        if (d->cout <= 32) { if (nk == 1) launch_tc_smallk<32, 1>(d, in, wgt, bias, residual, out, s); else launch_tc_smallk<32, 2>(d, in, wgt, bias, residual, out, s); }
+        else if (d->cout <= 64) { if (nk == 1) launch_tc_smallk<64, 1>(d, in, wgt, bias, residual, out, s); else launch_tc_smallk<64, 2>(d, in, wgt, bias, residual, out, s); }
+        else { if (nk == 1) launch_tc_smallk<128, 1>(d, in, wgt, bias, residual, out, s); else launch_tc_smallk<128, 2>(d, in, wgt, bias, residual, out, s); }
+        FM_CHECK_LAUNCH("fm_conv2d_tc(smallk)");
+        return FM_OK;
+    }
     // ring depth follows the K extent: short reductions (OSNet 1x1) want many co-resident CTAs, long ones (3x3 on
     // wide layers) want many slices of copies in flight
     if (d->cout <= 32) {
