@@ -14,6 +14,7 @@
 // PTX ISA "tcgen05 matrix / instruction descriptor" tables (cross-checked against cute/arch/mma_sm100_desc.hpp).
 #include "common.cuh"
 #include "../../include/fastmot_b200.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -578,7 +579,12 @@ extern "C" int fm_conv2d_tc(const FmConvDesc* d, const void* in, const void* wgt
     cudaStream_t s = (cudaStream_t)stream;
     const int nk = (d->kh * d->kw * d->cin + TC_BK - 1) / TC_BK;
     const int m_tiles_all = (d->n * d->ho * d->wo + TC_BM - 1) / TC_BM;
-    if (nk <= 2 && m_tiles_all >= 2 * FM_NUM_SMS) {      // big-M, tiny-K: persistent double-buffered variant
+    static int smallk_mode = -1;   // FM_CONV_SMALLK=0 disables, =1 (default) enables the persistent small-K variant
+    if (smallk_mode < 0) {
+        const char* e = getenv("FM_CONV_SMALLK");
+        smallk_mode = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (smallk_mode && nk <= 2 && m_tiles_all >= 2 * FM_NUM_SMS) {      // big-M, tiny-K: persistent variant
         if (d->cout <= 32) { if (nk == 1) launch_tc_smallk<32, 1>(d, in, wgt, bias, residual, out, s); else launch_tc_smallk<32, 2>(d, in, wgt, bias, residual, out, s); }
         else if (d->cout <= 64) { if (nk == 1) launch_tc_smallk<64, 1>(d, in, wgt, bias, residual, out, s); else launch_tc_smallk<64, 2>(d, in, wgt, bias, residual, out, s); }
         else { if (nk == 1) launch_tc_smallk<128, 1>(d, in, wgt, bias, residual, out, s); else launch_tc_smallk<128, 2>(d, in, wgt, bias, residual, out, s); }

@@ -1,0 +1,37 @@
+"""Micro-benchmark of the conv kernels on OSNet / YOLO layer shapes (CUDA events, L2 flushed between launches)."""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from fastmot_b200 import _lib
+from fastmot_b200.devmem import ptr, stream_ptr
+from fastmot_b200.engine import _conv_desc, _ensure_workspace
+lib = _lib.require_device()
+_ensure_workspace(lib, torch.device("cuda"))
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+SHAPES = [  # n, h, w, cin, cout, k, stride
+    (224, 64, 32, 64, 64, 1, 1), (224, 64, 32, 64, 256, 1, 1), (224, 64, 32, 256, 64, 1, 1), (224, 64, 32, 256, 256, 1, 1),
+    (224, 32, 16, 96, 96, 1, 1), (224, 32, 16, 96, 384, 1, 1), (224, 16, 8, 128, 128, 1, 1), (224, 256, 128, 8, 64, 7, 2),
+    (1, 80, 80, 128, 256, 3, 1), (1, 40, 40, 256, 512, 3, 1), (1, 20, 20, 512, 1024, 3, 1), (1, 160, 160, 64, 64, 3, 1),
+    (1, 320, 320, 32, 64, 3, 2), (1, 640, 640, 8, 32, 3, 1),
+]
+for (n, h, w, cin, cout, k, st) in SHAPES:
+    pad = k // 2
+    ho, wo = (h + 2 * pad - k) // st + 1, (w + 2 * pad - k) // st + 1
+    x = torch.randn(n, h, w, cin, device="cuda").half()
+    wt = torch.randn(cout, k, k, cin, device="cuda").half()
+    b = torch.zeros(cout, device="cuda")
+    y = torch.zeros(n, ho, wo, cout, device="cuda").half()
+    d = _conv_desc(n, h, w, cin, cin, 0, ho, wo, cout, cout, 0, k, st, pad, 5)
+    ts = []
+    for it in range(6):
+        flush.fill_(it)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lib.fm_conv2d_tc(C.byref(d), ptr(x), ptr(wt), ptr(b), None, ptr(y), stream_ptr())
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    us = sorted(ts[1:])[len(ts[1:]) // 2]
+    flops = 2.0 * n * ho * wo * cout * cin * k * k
+    byts = (x.numel() + y.numel() + wt.numel()) * 2
+    print(f"{(n,h,w,cin,cout,k,st)}: {us:8.1f} us  {flops/us/1e6:8.1f} TFLOP/s  {byts/us/1e3:7.1f} GB/s(min traffic)")
