@@ -111,6 +111,21 @@ __device__ __forceinline__ float tc_act(float v, int act) {
     }
 }
 
+__device__ unsigned long long* g_dbg_dev = nullptr;   // optional per-CTA phase timestamps (scripts/bench_conv.py)
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define DBG_STAMP(k)                                                                             \
+    do {                                                                                         \
+        if (g_dbg_dev && tid == 0) {                                                             \
+            const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);      \
+            if (cta < 4096) g_dbg_dev[cta * 8 + (k)] = gtimer();                                 \
+        }                                                                                        \
+    } while (0)
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half* __restrict__ in,
                                                        const __half* __restrict__ wgt, const float* __restrict__ bias,
@@ -125,6 +140,7 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    DBG_STAMP(0);
     const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
     const int M = d.n * d.ho * d.wo;
     const int Ktot = d.kh * d.kw * d.cin;
@@ -148,6 +164,7 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
+    DBG_STAMP(1);
 
     // ---- per-thread gather plan: chunk column c (16 B = 8 channels), rows (tid>>3) + 16*i ----
     const int c = tid & 7;
@@ -208,6 +225,7 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
         if (p < nk) issue_loads(p, p);
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    DBG_STAMP(2);
     for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % STAGES;
         const int kn = kb + STAGES - 1;
@@ -234,9 +252,11 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
             tc_commit(&bar_stage[s]);    // fires when the MMAs reading this stage are done
         }
     }
+    DBG_STAMP(3);
     if (tid == 0) tc_commit(&bar_done);
     mbar_wait(&bar_done, 0);
     tc_fence_after();
+    DBG_STAMP(4);
 
     // ---- epilogue: TMEM lane = tile row ----
     const int m = m0 + tid;
@@ -294,11 +314,13 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
             }
         }
     }
+    DBG_STAMP(5);
     tc_fence_before();
     __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "r"((uint32_t)(BN < 32 ? 32 : BN)));
+    DBG_STAMP(6);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -557,6 +579,12 @@ int launch_tc(const FmConvDesc* d, const void* in, const void* wgt, const float*
 }
 
 }  // namespace
+
+extern "C" int fm_conv_set_debug(void* dbg) {
+    unsigned long long* p = (unsigned long long*)dbg;
+    cudaMemcpyToSymbol(g_dbg_dev, &p, sizeof(p));
+    return FM_OK;
+}
 
 extern "C" int fm_conv_set_workspace(void* ws, long long bytes) {
     g_ws = (float*)ws;

@@ -8,6 +8,11 @@ from fastmot_b200.engine import _conv_desc, _ensure_workspace
 lib = _lib.require_device()
 _ensure_workspace(lib, torch.device("cuda"))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+DBG = "--dbg" in sys.argv
+dbg = torch.zeros(4096 * 8, dtype=torch.int64, device="cuda")
+lib.fm_conv_set_debug.argtypes = [C.c_void_p]
+if DBG:
+    lib.fm_conv_set_debug(C.c_void_p(dbg.data_ptr()))
 SHAPES = [  # n, h, w, cin, cout, k, stride
     (224, 64, 32, 64, 64, 1, 1), (224, 64, 32, 64, 256, 1, 1), (224, 64, 32, 256, 64, 1, 1), (224, 64, 32, 256, 256, 1, 1),
     (224, 32, 16, 96, 96, 1, 1), (224, 32, 16, 96, 384, 1, 1), (224, 16, 8, 128, 128, 1, 1), (224, 256, 128, 8, 64, 7, 2),
@@ -34,4 +39,12 @@ for (n, h, w, cin, cout, k, st) in SHAPES:
     us = sorted(ts[1:])[len(ts[1:]) // 2]
     flops = 2.0 * n * ho * wo * cout * cin * k * k
     byts = (x.numel() + y.numel() + wt.numel()) * 2
+    if DBG:
+        t = dbg.cpu().numpy().reshape(4096, 8)
+        t = t[t[:, 0] > 0]
+        t0 = t[:, 0].min()
+        ph = (t[:, 1:7] - t[:, 0:6]).mean(0)
+        print("   CTAs", len(t), "span(us)", (t[:, 6].max() - t0) / 1e3, "start spread(us)", (t[:, 0].max() - t0) / 1e3,
+              "phases ns [alloc+sync, plan+prologue, mainloop, commit-wait, epilogue, dealloc]:", [int(x) for x in ph])
+        dbg.zero_()
     print(f"{(n,h,w,cin,cout,k,st)}: {us:8.1f} us  {flops/us/1e6:8.1f} TFLOP/s  {byts/us/1e3:7.1f} GB/s(min traffic)")
