@@ -126,6 +126,66 @@ __device__ __forceinline__ unsigned long long gtimer() {
         }                                                                                        \
     } while (0)
 
+// Epilogue for 32 consecutive output channels of one pixel row: bias + activation (+ residual) and fp16 NHWC store.
+// Stores are 32 bytes per thread (st.global.v8.b32 = one full DRAM sector) whenever the slice is 32-byte aligned:
+// 16-byte stores to rows that are hundreds of bytes apart are partial-sector writes and were measured to make the
+// epilogue 20-60 us per CTA (profiles/r01_conv_phase_timing.md).
+__device__ __forceinline__ void epilogue_store32(float* v32, size_t m, int n_base, const FmConvDesc& d,
+                                                 const float* __restrict__ bias, const __half* __restrict__ residual,
+                                                 __half* __restrict__ out, int act, bool res_first) {
+    const bool al16 = ((d.cout_stride | d.cout_offset) & 15) == 0;
+    const bool res16 = residual != nullptr && ((d.res_stride | d.res_offset) & 15) == 0;
+#pragma unroll
+    for (int jj = 0; jj < 32; jj += 16) {
+        const int n = n_base + jj;
+        if (n >= d.cout) break;
+        float* v = v32 + jj;
+        const bool full = n + 16 <= d.cout;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const float x = v[q] + ((bias && (full || n + q < d.cout)) ? bias[n + q] : 0.f);
+            v[q] = res_first ? x : tc_act(x, act);
+        }
+        __half* op = out + m * d.cout_stride + d.cout_offset + n;
+        if (full && al16) {
+            if (residual) {
+                const __half* rp = residual + m * d.res_stride + d.res_offset + n;
+                if (res16) {
+                    uint32_t r[8];
+                    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                                 : "l"(rp));
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&r[q]));
+                        v[2 * q] += f.x; v[2 * q + 1] += f.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) v[q] += __half2float(rp[q]);
+                }
+            }
+            uint32_t w[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float a = res_first ? tc_act(v[2 * q], act) : v[2 * q];
+                const float b = res_first ? tc_act(v[2 * q + 1], act) : v[2 * q + 1];
+                const __half2 h = __floats2half2_rn(a, b);
+                w[q] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(op), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                         "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                         : "memory");
+        } else {
+            for (int q = 0; q < 16 && n + q < d.cout; ++q) {
+                float x = v[q];
+                if (residual) x += __half2float(residual[m * d.res_stride + d.res_offset + n + q]);
+                op[q] = __float2half(res_first ? tc_act(x, act) : x);
+            }
+        }
+    }
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half* __restrict__ in,
                                                        const __half* __restrict__ wgt, const float* __restrict__ bias,
@@ -261,10 +321,8 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
     // ---- epilogue: TMEM lane = tile row ----
     const int m = m0 + tid;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const bool vec_ok = ((d.cout_stride | d.cout_offset) & 7) == 0;
     const int act = d.act & 0xff;
     const bool res_first = (d.act & FM_ACT_AFTER_RESIDUAL) != 0;   // act(conv + residual) instead of act(conv) + residual
-    const bool res_vec = residual != nullptr && ((d.res_stride | d.res_offset) & 7) == 0;
 #pragma unroll 1
     for (int j0 = 0; j0 < BN; j0 += 32) {
         float v32[32];
@@ -272,47 +330,23 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
         if (m >= M) continue;
         if (gridDim.z > 1) {              // raw fp32 partials; bias / activation happen in splitk_reduce_kernel
             float* wp = ws + ((size_t)blockIdx.z * M + m) * d.cout + n0 + j0;
+            if (n0 + j0 + 32 <= d.cout && (d.cout & 7) == 0) {      // full-sector (32-byte) stores
 #pragma unroll
-            for (int q = 0; q < 32; ++q)
-                if (n0 + j0 + q < d.cout) wp[q] = v32[q];
+                for (int q = 0; q < 32; q += 8)
+                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(wp + q),
+                                 "r"(__float_as_uint(v32[q])), "r"(__float_as_uint(v32[q + 1])),
+                                 "r"(__float_as_uint(v32[q + 2])), "r"(__float_as_uint(v32[q + 3])),
+                                 "r"(__float_as_uint(v32[q + 4])), "r"(__float_as_uint(v32[q + 5])),
+                                 "r"(__float_as_uint(v32[q + 6])), "r"(__float_as_uint(v32[q + 7]))
+                                 : "memory");
+            } else {
+#pragma unroll
+                for (int q = 0; q < 32; ++q)
+                    if (n0 + j0 + q < d.cout) wp[q] = v32[q];
+            }
             continue;
         }
-#pragma unroll
-        for (int jj = 0; jj < 32; jj += 8) {
-            const int n = n0 + j0 + jj;
-            if (n >= d.cout) break;
-            float* v = v32 + jj;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                float x = v[q] + ((bias && n + q < d.cout) ? bias[n + q] : 0.f);
-                v[q] = res_first ? x : tc_act(x, act);
-            }
-            __half* op = out + (size_t)m * d.cout_stride + d.cout_offset + n;
-            if (n + 8 <= d.cout && vec_ok) {
-                if (residual) {
-                    const __half* rp = residual + (size_t)m * d.res_stride + d.res_offset + n;
-                    if (res_vec) {
-                        const int4 rv = *(const int4*)rp;
-                        const __half* rh = (const __half*)&rv;
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) v[q] += __half2float(rh[q]);
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) v[q] += __half2float(rp[q]);
-                    }
-                }
-                __align__(16) __half h[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) h[q] = __float2half(res_first ? tc_act(v[q], act) : v[q]);
-                *(int4*)op = *(const int4*)h;
-            } else {
-                for (int q = 0; q < 8 && n + q < d.cout; ++q) {
-                    float x = v[q];
-                    if (residual) x += __half2float(residual[(size_t)m * d.res_stride + d.res_offset + n + q]);
-                    op[q] = __float2half(res_first ? tc_act(x, act) : x);
-                }
-            }
-        }
+        epilogue_store32(v32, (size_t)m, n0 + j0, d, bias, residual, out, act, res_first);
     }
     DBG_STAMP(5);
     tc_fence_before();
@@ -411,8 +445,6 @@ __global__ void __launch_bounds__(128) conv_tc_smallk_kernel(FmConvDesc d, const
     int tile = blockIdx.x;
     if (tile < m_tiles) load_A(tile, 0);
     asm volatile("cp.async.commit_group;" ::: "memory");
-    const bool vec_ok = ((d.cout_stride | d.cout_offset) & 7) == 0;
-    const bool res_vec = residual != nullptr && ((d.res_stride | d.res_offset) & 7) == 0;
     const int act = d.act & 0xff;
     const bool res_first = (d.act & FM_ACT_AFTER_RESIDUAL) != 0;
     int it = 0;
@@ -447,42 +479,7 @@ __global__ void __launch_bounds__(128) conv_tc_smallk_kernel(FmConvDesc d, const
             float v32[32];
             tmem_ld32(lane_addr + j0, v32);
             if (m >= M) continue;
-#pragma unroll
-            for (int jj = 0; jj < 32; jj += 8) {
-                const int n = n0 + j0 + jj;
-                if (n >= d.cout) break;
-                float* v = v32 + jj;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    float x = v[q] + ((bias && n + q < d.cout) ? bias[n + q] : 0.f);
-                    v[q] = res_first ? x : tc_act(x, act);
-                }
-                __half* op = out + (size_t)m * d.cout_stride + d.cout_offset + n;
-                if (n + 8 <= d.cout && vec_ok) {
-                    if (residual) {
-                        const __half* rp = residual + (size_t)m * d.res_stride + d.res_offset + n;
-                        if (res_vec) {
-                            const int4 rv = *(const int4*)rp;
-                            const __half* rh = (const __half*)&rv;
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) v[q] += __half2float(rh[q]);
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) v[q] += __half2float(rp[q]);
-                        }
-                    }
-                    __align__(16) __half h[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) h[q] = __float2half(res_first ? tc_act(v[q], act) : v[q]);
-                    *(int4*)op = *(const int4*)h;
-                } else {
-                    for (int q = 0; q < 8 && n + q < d.cout; ++q) {
-                        float x = v[q];
-                        if (residual) x += __half2float(residual[(size_t)m * d.res_stride + d.res_offset + n + q]);
-                        op[q] = __float2half(res_first ? tc_act(x, act) : x);
-                    }
-                }
-            }
+            epilogue_store32(v32, (size_t)m, n0 + j0, d, bias, residual, out, act, res_first);
         }
         tc_fence_before();
         __syncthreads();      // all TMEM reads of accumulator `buf` done before it is overwritten two tiles later
