@@ -130,57 +130,64 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // Stores are 32 bytes per thread (st.global.v8.b32 = one full DRAM sector) whenever the slice is 32-byte aligned:
 // 16-byte stores to rows that are hundreds of bytes apart are partial-sector writes and were measured to make the
 // epilogue 20-60 us per CTA (profiles/r01_conv_phase_timing.md).
-__device__ __forceinline__ void epilogue_store32(float* v32, size_t m, int n_base, const FmConvDesc& d,
+__device__ __forceinline__ void epilogue_store32(float (&v32)[32], size_t m, int n_base, const FmConvDesc& d,
                                                  const float* __restrict__ bias, const __half* __restrict__ residual,
                                                  __half* __restrict__ out, int act, bool res_first) {
+    // every index into v32 is a compile-time constant after unrolling: the accumulators must stay in registers
+    // (a first version indexed them dynamically and the epilogue ran out of local memory)
     const bool al16 = ((d.cout_stride | d.cout_offset) & 15) == 0;
     const bool res16 = residual != nullptr && ((d.res_stride | d.res_offset) & 15) == 0;
 #pragma unroll
-    for (int jj = 0; jj < 32; jj += 16) {
-        const int n = n_base + jj;
-        if (n >= d.cout) break;
-        float* v = v32 + jj;
-        const bool full = n + 16 <= d.cout;
+    for (int hh = 0; hh < 2; ++hh) {
+        const int n = n_base + hh * 16;
+        if (n < d.cout) {
+            const bool full = n + 16 <= d.cout;
+            float v[16];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const float x = v[q] + ((bias && (full || n + q < d.cout)) ? bias[n + q] : 0.f);
-            v[q] = res_first ? x : tc_act(x, act);
-        }
-        __half* op = out + m * d.cout_stride + d.cout_offset + n;
-        if (full && al16) {
-            if (residual) {
-                const __half* rp = residual + m * d.res_stride + d.res_offset + n;
-                if (res16) {
-                    uint32_t r[8];
-                    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                                 : "l"(rp));
+            for (int q = 0; q < 16; ++q) {
+                const float x = v32[hh * 16 + q] + ((bias && (full || n + q < d.cout)) ? bias[n + q] : 0.f);
+                v[q] = res_first ? x : tc_act(x, act);
+            }
+            __half* op = out + m * d.cout_stride + d.cout_offset + n;
+            if (full && al16) {
+                if (residual) {
+                    const __half* rp = residual + m * d.res_stride + d.res_offset + n;
+                    if (res16) {
+                        uint32_t r[8];
+                        asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+                                       "=r"(r[7])
+                                     : "l"(rp));
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&r[q]));
-                        v[2 * q] += f.x; v[2 * q + 1] += f.y;
+                        for (int q = 0; q < 8; ++q) {
+                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&r[q]));
+                            v[2 * q] += f.x; v[2 * q + 1] += f.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) v[q] += __half2float(rp[q]);
                     }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) v[q] += __half2float(rp[q]);
                 }
-            }
-            uint32_t w[8];
+                uint32_t w[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float a = res_first ? tc_act(v[2 * q], act) : v[2 * q];
-                const float b = res_first ? tc_act(v[2 * q + 1], act) : v[2 * q + 1];
-                const __half2 h = __floats2half2_rn(a, b);
-                w[q] = *reinterpret_cast<const uint32_t*>(&h);
-            }
-            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(op), "r"(w[0]), "r"(w[1]), "r"(w[2]),
-                         "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
-                         : "memory");
-        } else {
-            for (int q = 0; q < 16 && n + q < d.cout; ++q) {
-                float x = v[q];
-                if (residual) x += __half2float(residual[m * d.res_stride + d.res_offset + n + q]);
-                op[q] = __float2half(res_first ? tc_act(x, act) : x);
+                for (int q = 0; q < 8; ++q) {
+                    const float a = res_first ? tc_act(v[2 * q], act) : v[2 * q];
+                    const float b = res_first ? tc_act(v[2 * q + 1], act) : v[2 * q + 1];
+                    const __half2 h = __floats2half2_rn(a, b);
+                    w[q] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(op), "r"(w[0]), "r"(w[1]),
+                             "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                             : "memory");
+            } else {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    if (n + q < d.cout) {
+                        float x = v[q];
+                        if (residual) x += __half2float(residual[m * d.res_stride + d.res_offset + n + q]);
+                        op[q] = __float2half(res_first ? tc_act(x, act) : x);
+                    }
+                }
             }
         }
     }
