@@ -334,6 +334,7 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
     for (int j0 = 0; j0 < BN; j0 += 32) {
         float v32[32];
         tmem_ld32(lane_addr + j0, v32);   // warp-collective: every lane executes it
+        if (j0 == 0) DBG_STAMP(7);
         if (m >= M) continue;
         if (gridDim.z > 1) {              // raw fp32 partials; bias / activation happen in splitk_reduce_kernel
             float* wp = ws + ((size_t)blockIdx.z * M + m) * d.cout + n0 + j0;

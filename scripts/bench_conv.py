@@ -45,6 +45,7 @@ for (n, h, w, cin, cout, k, st) in SHAPES:
         t0 = t[:, 0].min()
         ph = (t[:, 1:7] - t[:, 0:6]).mean(0)
         print("   CTAs", len(t), "span(us)", (t[:, 6].max() - t0) / 1e3, "start spread(us)", (t[:, 0].max() - t0) / 1e3,
-              "phases ns [alloc+sync, plan+prologue, mainloop, commit-wait, epilogue, dealloc]:", [int(x) for x in ph])
+              "phases ns [alloc+sync, plan+prologue, mainloop, commit-wait, epilogue, dealloc]:", [int(x) for x in ph],
+              "first tmem_ld32 ns:", int((t[:, 7] - t[:, 4]).mean()))
         dbg.zero_()
     print(f"{(n,h,w,cin,cout,k,st)}: {us:8.1f} us  {flops/us/1e6:8.1f} TFLOP/s  {byts/us/1e3:7.1f} GB/s(min traffic)")
