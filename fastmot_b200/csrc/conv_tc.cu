@@ -329,32 +329,95 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
     const int m = m0 + tid;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     const int act = d.act & 0xff;
-    const bool res_first = (d.act & FM_ACT_AFTER_RESIDUAL) != 0;   // act(conv + residual) instead of act(conv) + residual
+    const bool res_first = (d.act & FM_ACT_AFTER_RESIDUAL) != 0;
+    const bool staged = gridDim.z == 1 && ((d.cout_stride | d.cout_offset | d.cout) & 7) == 0 &&
+                        (residual == nullptr || ((d.res_stride | d.res_offset) & 7) == 0);
+    if (staged) {
+        // A thread owns one output ROW; writing it straight out makes every warp store touch 32 different lines
+        // (measured: 15-60 us of LSU replays per CTA).  Stage the warp's 32 x BN tile in shared memory (the ring
+        // buffers are idle now) and write it back with lanes running along the channels: each store instruction
+        // covers whole rows.
+        constexpr int PITCH = BN * 2 + 16;                       // bytes, +16 keeps the column writes conflict-free
+        uint8_t* stg = smem + (size_t)warp * 32 * PITCH;
+        const int lane = tid & 31;
 #pragma unroll 1
-    for (int j0 = 0; j0 < BN; j0 += 32) {
-        float v32[32];
-        tmem_ld32(lane_addr + j0, v32);   // warp-collective: every lane executes it
-        if (j0 == 0) DBG_STAMP(7);
-        if (m >= M) continue;
-        if (gridDim.z > 1) {              // raw fp32 partials; bias / activation happen in splitk_reduce_kernel
-            float* wp = ws + ((size_t)blockIdx.z * M + m) * d.cout + n0 + j0;
-            if (n0 + j0 + 32 <= d.cout && (d.cout & 7) == 0) {      // full-sector (32-byte) stores
+        for (int j0 = 0; j0 < BN; j0 += 32) {
+            float v32[32];
+            tmem_ld32(lane_addr + j0, v32);
+            if (j0 == 0) DBG_STAMP(7);
 #pragma unroll
-                for (int q = 0; q < 32; q += 8)
-                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(wp + q),
-                                 "r"(__float_as_uint(v32[q])), "r"(__float_as_uint(v32[q + 1])),
-                                 "r"(__float_as_uint(v32[q + 2])), "r"(__float_as_uint(v32[q + 3])),
-                                 "r"(__float_as_uint(v32[q + 4])), "r"(__float_as_uint(v32[q + 5])),
-                                 "r"(__float_as_uint(v32[q + 6])), "r"(__float_as_uint(v32[q + 7]))
-                                 : "memory");
-            } else {
+            for (int q0 = 0; q0 < 32; q0 += 8) {
+                uint32_t w[4];
 #pragma unroll
-                for (int q = 0; q < 32; ++q)
-                    if (n0 + j0 + q < d.cout) wp[q] = v32[q];
+                for (int q = 0; q < 4; ++q) {
+                    const int n = n0 + j0 + q0 + 2 * q;
+                    float a = v32[q0 + 2 * q] + ((bias && n < d.cout) ? bias[n] : 0.f);
+                    float b2 = v32[q0 + 2 * q + 1] + ((bias && n + 1 < d.cout) ? bias[n + 1] : 0.f);
+                    if (!res_first) { a = tc_act(a, act); b2 = tc_act(b2, act); }
+                    const __half2 h = __floats2half2_rn(a, b2);
+                    w[q] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                *reinterpret_cast<uint4*>(stg + lane * PITCH + (j0 + q0) * 2) = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            continue;
         }
-        epilogue_store32(v32, (size_t)m, n0 + j0, d, bias, residual, out, act, res_first);
+        __syncwarp();
+        constexpr int CPR = BN / 8;                  // 16-byte chunks per row
+        constexpr int RPI = 32 / CPR > 0 ? 32 / CPR : 1;   // rows per store instruction
+        const int chunk = lane % CPR, rsub = lane / CPR;
+#pragma unroll 1
+        for (int r0 = 0; r0 < 32; r0 += RPI) {
+            const int row = r0 + rsub;
+            const int mm = m0 + warp * 32 + row;
+            const int n = n0 + chunk * 8;
+            if (CPR > 32 && false) {}
+            if (row < 32 && mm < M && n < d.cout) {
+                uint4 pk = *reinterpret_cast<const uint4*>(stg + row * PITCH + chunk * 16);
+                if (residual) {
+                    const uint4 rv = *reinterpret_cast<const uint4*>(residual + (size_t)mm * d.res_stride + d.res_offset + n);
+                    const __half2* ph = reinterpret_cast<const __half2*>(&pk);
+                    const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+                    uint32_t w[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float2 x = __half22float2(ph[q]);
+                        const float2 r = __half22float2(rh[q]);
+                        x.x += r.x; x.y += r.y;
+                        if (res_first) { x.x = tc_act(x.x, act); x.y = tc_act(x.y, act); }
+                        const __half2 h = __floats2half2_rn(x.x, x.y);
+                        w[q] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    pk = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                *reinterpret_cast<uint4*>(out + (size_t)mm * d.cout_stride + d.cout_offset + n) = pk;
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int j0 = 0; j0 < BN; j0 += 32) {
+            float v32[32];
+            tmem_ld32(lane_addr + j0, v32);   // warp-collective: every lane executes it
+            if (j0 == 0) DBG_STAMP(7);
+            if (m >= M) continue;
+            if (gridDim.z > 1) {              // raw fp32 partials; bias / activation happen in splitk_reduce_kernel
+                float* wp = ws + ((size_t)blockIdx.z * M + m) * d.cout + n0 + j0;
+                if (n0 + j0 + 32 <= d.cout && (d.cout & 7) == 0) {      // full-sector (32-byte) stores
+#pragma unroll
+                    for (int q = 0; q < 32; q += 8)
+                        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(wp + q),
+                                     "r"(__float_as_uint(v32[q])), "r"(__float_as_uint(v32[q + 1])),
+                                     "r"(__float_as_uint(v32[q + 2])), "r"(__float_as_uint(v32[q + 3])),
+                                     "r"(__float_as_uint(v32[q + 4])), "r"(__float_as_uint(v32[q + 5])),
+                                     "r"(__float_as_uint(v32[q + 6])), "r"(__float_as_uint(v32[q + 7]))
+                                     : "memory");
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q)
+                        if (n0 + j0 + q < d.cout) wp[q] = v32[q];
+                }
+                continue;
+            }
+            epilogue_store32(v32, (size_t)m, n0 + j0, d, bias, residual, out, act, res_first);
+        }
     }
     DBG_STAMP(5);
     tc_fence_before();
@@ -551,7 +614,9 @@ long long g_ws_bytes = 0;
 template <int BN, int STAGES>
 int launch_tc(const FmConvDesc* d, const void* in, const void* wgt, const float* bias, const void* residual, void* out,
               cudaStream_t s) {
-    constexpr int smem = STAGES * (TC_BM * 128 + BN * 128) + 1024;
+    // the ring doubles as the epilogue's staging tile (4 warps x 32 rows x (BN*2+16) bytes)
+    constexpr int ring = STAGES * (TC_BM * 128 + BN * 128), stg = 4 * 32 * (BN * 2 + 16);
+    constexpr int smem = (ring > stg ? ring : stg) + 1024;
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -612,10 +677,10 @@ extern "C" int fm_conv2d_tc(const FmConvDesc* d, const void* in, const void* wgt
     cudaStream_t s = (cudaStream_t)stream;
     const int nk = (d->kh * d->kw * d->cin + TC_BK - 1) / TC_BK;
     const int m_tiles_all = (d->n * d->ho * d->wo + TC_BM - 1) / TC_BM;
-    static int smallk_mode = -1;   // FM_CONV_SMALLK=0 disables, =1 (default) enables the persistent small-K variant
+    static int smallk_mode = -1;   // FM_CONV_SMALLK=1 enables the persistent small-K variant (experimental)
     if (smallk_mode < 0) {
         const char* e = getenv("FM_CONV_SMALLK");
-        smallk_mode = (e && e[0] == '0') ? 0 : 1;
+        smallk_mode = (e && e[0] == '1') ? 1 : 0;   // measured slower than the tile-per-CTA kernel: off by default
     }
     if (smallk_mode && nk <= 2 && m_tiles_all >= 2 * FM_NUM_SMS) {      // big-M, tiny-K: persistent variant
         if (d->cout <= 32) { if (nk == 1) launch_tc_smallk<32, 1>(d, in, wgt, bias, residual, out, s); else launch_tc_smallk<32, 2>(d, in, wgt, bias, residual, out, s); }
@@ -626,14 +691,21 @@ extern "C" int fm_conv2d_tc(const FmConvDesc* d, const void* in, const void* wgt
     }
     // ring depth follows the K extent: short reductions (OSNet 1x1) want many co-resident CTAs, long ones (3x3 on
     // wide layers) want many slices of copies in flight
-    if (d->cout <= 32) {
-        if (nk <= 2) launch_tc<32, 2>(d, in, wgt, bias, residual, out, s);
+    static int force_bn = -1;      // FM_CONV_BN=32|64|128 overrides the tile width (experiments only)
+    if (force_bn < 0) { const char* e = getenv("FM_CONV_BN"); force_bn = e ? atoi(e) : 0; }
+    int bn = d->cout <= 32 ? 32 : d->cout <= 64 ? 64 : 128;
+    if (force_bn) bn = force_bn;
+    if (bn == 32) {
+        if (nk == 1) launch_tc<32, 1>(d, in, wgt, bias, residual, out, s);
+        else if (nk <= 2) launch_tc<32, 2>(d, in, wgt, bias, residual, out, s);
         else launch_tc<32, 4>(d, in, wgt, bias, residual, out, s);
-    } else if (d->cout <= 64) {
-        if (nk <= 2) launch_tc<64, 2>(d, in, wgt, bias, residual, out, s);
+    } else if (bn == 64) {
+        if (nk == 1) launch_tc<64, 1>(d, in, wgt, bias, residual, out, s);
+        else if (nk <= 2) launch_tc<64, 2>(d, in, wgt, bias, residual, out, s);
         else launch_tc<64, 4>(d, in, wgt, bias, residual, out, s);
     } else {
-        if (nk <= 2) launch_tc<128, 2>(d, in, wgt, bias, residual, out, s);
+        if (nk == 1) launch_tc<128, 1>(d, in, wgt, bias, residual, out, s);
+        else if (nk <= 2) launch_tc<128, 2>(d, in, wgt, bias, residual, out, s);
         else if (nk < 6) launch_tc<128, 3>(d, in, wgt, bias, residual, out, s);
         else launch_tc<128, 6>(d, in, wgt, bias, residual, out, s);
     }
