@@ -100,14 +100,48 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ float tc_mish(float v) {
+    // x * tanh(softplus(x)) with n = e^x:  tanh(log(1+n)) = n(n+2) / (n(n+2) + 2)  -- one ex2, one rcp, no cancellation
+    const float n = __expf(fminf(v, 20.f));
+    const float t = n * (n + 2.f);
+    return v > 20.f ? v : v * __fdividef(t, t + 2.f);
+}
+
 __device__ __forceinline__ float tc_act(float v, int act) {
     switch (act) {
         case FM_ACT_LEAKY: return v > 0.f ? v : 0.1f * v;
-        case FM_ACT_RELU: return v > 0.f ? v : 0.f;
-        case FM_ACT_MISH: { float sp = v > 20.f ? v : log1pf(__expf(v)); return v * tanhf(sp); }
-        case FM_ACT_SWISH: return v / (1.f + __expf(-v));
-        case FM_ACT_LOGISTIC: return 1.f / (1.f + __expf(-v));
+        case FM_ACT_RELU: return fmaxf(v, 0.f);
+        case FM_ACT_MISH: return tc_mish(v);
+        case FM_ACT_SWISH: return __fdividef(v, 1.f + __expf(-v));
+        case FM_ACT_LOGISTIC: return __fdividef(1.f, 1.f + __expf(-v));
         default: return v;
+    }
+}
+
+// activation of 8 values with the (warp-uniform) switch hoisted out of the element loop
+__device__ __forceinline__ void tc_act8(float (&v)[8], int act) {
+    switch (act) {
+        case FM_ACT_LEAKY:
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = v[q] > 0.f ? v[q] : 0.1f * v[q];
+            break;
+        case FM_ACT_RELU:
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
+            break;
+        case FM_ACT_MISH:
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = tc_mish(v[q]);
+            break;
+        case FM_ACT_SWISH:
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = __fdividef(v[q], 1.f + __expf(-v[q]));
+            break;
+        case FM_ACT_LOGISTIC:
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = __fdividef(1.f, 1.f + __expf(-v[q]));
+            break;
+        default: break;
     }
 }
 
@@ -193,6 +227,88 @@ __device__ __forceinline__ void epilogue_store32(float (&v32)[32], size_t m, int
     }
 }
 
+
+// Staged epilogue of one warp's 32 x BN accumulator slab.  A thread owns one output ROW in TMEM; writing it straight
+// out makes every warp store touch 32 different lines (measured: 15-60 us of LSU replays per CTA).  The slab goes
+// through shared memory instead and is written back with lanes running along the channels, so each store
+// instruction covers whole rows.  Needs 8-channel alignment of the output / residual views.
+template <int BN>
+__device__ __forceinline__ void epilogue_staged(uint8_t* stg, uint32_t lane_addr, int lane, int m_warp0, int n0, int M,
+                                                const FmConvDesc& d, const float* __restrict__ bias,
+                                                const __half* __restrict__ residual, __half* __restrict__ out,
+                                                int act, bool res_first) {
+    constexpr int PITCH = BN * 2 + 16;           // bytes; +16 keeps the per-row 16-byte writes conflict-free
+    // phase 1: raw accumulators -> fp16 -> smem (row per lane).  Bias / activation wait for phase 2, where a lane
+    // keeps the same 8 channels for every row and so loads its bias once.
+#pragma unroll 1
+    for (int j0 = 0; j0 < BN; j0 += 32) {
+        float v32[32];
+        tmem_ld32(lane_addr + j0, v32);
+#pragma unroll
+        for (int q0 = 0; q0 < 32; q0 += 8) {
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const __half2 h = __floats2half2_rn(v32[q0 + 2 * q], v32[q0 + 2 * q + 1]);
+                w[q] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(stg + lane * PITCH + (j0 + q0) * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    __syncwarp();
+    constexpr int CPR = BN / 8;                  // 16-byte chunks per row
+    constexpr int RPI = 32 / CPR;                // rows per store instruction
+    const int chunk = lane % CPR, rsub = lane / CPR;
+    const int n = n0 + chunk * 8;
+    if (n < d.cout) {                            // cout % 8 == 0 (staged_ok): the whole chunk is in range
+        float b8[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) b8[q] = bias ? bias[n + q] : 0.f;
+        const __half* rp = residual ? residual + d.res_offset + n : nullptr;
+        __half* op = out + d.cout_offset + n;
+#pragma unroll 2
+        for (int r0 = 0; r0 < 32; r0 += RPI) {
+            const int row = r0 + rsub;
+            const int mm = m_warp0 + row;
+            if (mm >= M) break;
+            const uint4 pk = *reinterpret_cast<const uint4*>(stg + row * PITCH + chunk * 16);
+            const __half2* ph = reinterpret_cast<const __half2*>(&pk);
+            float x[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 f = __half22float2(ph[q]);
+                x[2 * q] = f.x + b8[2 * q];
+                x[2 * q + 1] = f.y + b8[2 * q + 1];
+            }
+            if (!res_first) tc_act8(x, act);
+            if (rp) {
+                const uint4 rv = *reinterpret_cast<const uint4*>(rp + (size_t)mm * d.res_stride);
+                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 f = __half22float2(rh[q]);
+                    x[2 * q] += f.x;
+                    x[2 * q + 1] += f.y;
+                }
+            }
+            if (res_first) tc_act8(x, act);
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const __half2 h = __floats2half2_rn(x[2 * q], x[2 * q + 1]);
+                w[q] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(op + (size_t)mm * d.cout_stride) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ bool staged_ok(const FmConvDesc& d, const void* residual) {
+    return ((d.cout_stride | d.cout_offset | d.cout) & 7) == 0 &&
+           (residual == nullptr || ((d.res_stride | d.res_offset) & 7) == 0);
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half* __restrict__ in,
                                                        const __half* __restrict__ wgt, const float* __restrict__ bias,
@@ -237,10 +353,14 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
     const int c = tid & 7;
     const int rbase = tid >> 3;
     int pn[8], ph[8], pw[8];
+    // 1x1 / stride 1 / no padding: input pixel == output pixel, no index arithmetic at all
+    const bool pointwise = d.kh == 1 && d.kw == 1 && d.stride == 1 && d.pad == 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int m = m0 + rbase + 16 * i;
-        if (m < M) {
+        if (pointwise) {
+            pn[i] = m < M ? 0 : -1; ph[i] = 0; pw[i] = 0;
+        } else if (m < M) {
             const int wo = m % d.wo, t = m / d.wo, ho = t % d.ho;
             pn[i] = t / d.ho;
             ph[i] = ho * d.stride - d.pad;
@@ -258,6 +378,17 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
         uint8_t* sB = sA + A_BYTES;
         const int kelem = (kb0 + kb) * TC_BK + c * 8;
         const bool kvalid = kelem < Ktot;
+        if (pointwise) {
+            const __half* base = in + d.cin_offset + (kvalid ? kelem : 0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = rbase + 16 * i;
+                const bool ok = kvalid && pn[i] >= 0;
+                const __half* src = ok ? base + (size_t)(m0 + r) * d.cin_stride : in;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sA + r * 128 + ((c ^ (r & 7)) << 4))),
+                             "l"(src), "r"(ok ? 16u : 0u));
+            }
+        } else {
         const int tap = kvalid ? kelem / d.cin : 0;
         const int cch = kvalid ? kelem - tap * d.cin : 0;
         const int fr = tap / d.kw, fs = tap - fr * d.kw;
@@ -275,6 +406,7 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
             }
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sA + r * 128 + ((c ^ (r & 7)) << 4))),
                          "l"(src), "r"(bytes));
+        }
         }
 #pragma unroll
         for (int i = 0; i < BN / 16; ++i) {
@@ -330,67 +462,11 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     const int act = d.act & 0xff;
     const bool res_first = (d.act & FM_ACT_AFTER_RESIDUAL) != 0;
-    const bool staged = gridDim.z == 1 && ((d.cout_stride | d.cout_offset | d.cout) & 7) == 0 &&
-                        (residual == nullptr || ((d.res_stride | d.res_offset) & 7) == 0);
+    const bool staged = gridDim.z == 1 && staged_ok(d, residual);
     if (staged) {
-        // A thread owns one output ROW; writing it straight out makes every warp store touch 32 different lines
-        // (measured: 15-60 us of LSU replays per CTA).  Stage the warp's 32 x BN tile in shared memory (the ring
-        // buffers are idle now) and write it back with lanes running along the channels: each store instruction
-        // covers whole rows.
-        constexpr int PITCH = BN * 2 + 16;                       // bytes, +16 keeps the column writes conflict-free
-        uint8_t* stg = smem + (size_t)warp * 32 * PITCH;
-        const int lane = tid & 31;
-#pragma unroll 1
-        for (int j0 = 0; j0 < BN; j0 += 32) {
-            float v32[32];
-            tmem_ld32(lane_addr + j0, v32);
-            if (j0 == 0) DBG_STAMP(7);
-#pragma unroll
-            for (int q0 = 0; q0 < 32; q0 += 8) {
-                uint32_t w[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int n = n0 + j0 + q0 + 2 * q;
-                    float a = v32[q0 + 2 * q] + ((bias && n < d.cout) ? bias[n] : 0.f);
-                    float b2 = v32[q0 + 2 * q + 1] + ((bias && n + 1 < d.cout) ? bias[n + 1] : 0.f);
-                    if (!res_first) { a = tc_act(a, act); b2 = tc_act(b2, act); }
-                    const __half2 h = __floats2half2_rn(a, b2);
-                    w[q] = *reinterpret_cast<const uint32_t*>(&h);
-                }
-                *reinterpret_cast<uint4*>(stg + lane * PITCH + (j0 + q0) * 2) = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-        }
-        __syncwarp();
-        constexpr int CPR = BN / 8;                  // 16-byte chunks per row
-        constexpr int RPI = 32 / CPR > 0 ? 32 / CPR : 1;   // rows per store instruction
-        const int chunk = lane % CPR, rsub = lane / CPR;
-#pragma unroll 1
-        for (int r0 = 0; r0 < 32; r0 += RPI) {
-            const int row = r0 + rsub;
-            const int mm = m0 + warp * 32 + row;
-            const int n = n0 + chunk * 8;
-            if (CPR > 32 && false) {}
-            if (row < 32 && mm < M && n < d.cout) {
-                uint4 pk = *reinterpret_cast<const uint4*>(stg + row * PITCH + chunk * 16);
-                if (residual) {
-                    const uint4 rv = *reinterpret_cast<const uint4*>(residual + (size_t)mm * d.res_stride + d.res_offset + n);
-                    const __half2* ph = reinterpret_cast<const __half2*>(&pk);
-                    const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-                    uint32_t w[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float2 x = __half22float2(ph[q]);
-                        const float2 r = __half22float2(rh[q]);
-                        x.x += r.x; x.y += r.y;
-                        if (res_first) { x.x = tc_act(x.x, act); x.y = tc_act(x.y, act); }
-                        const __half2 h = __floats2half2_rn(x.x, x.y);
-                        w[q] = *reinterpret_cast<const uint32_t*>(&h);
-                    }
-                    pk = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-                *reinterpret_cast<uint4*>(out + (size_t)mm * d.cout_stride + d.cout_offset + n) = pk;
-            }
-        }
+        // the ring buffers are idle now: reuse them as the staging tile
+        epilogue_staged<BN>(smem + (size_t)warp * 32 * (BN * 2 + 16), lane_addr, tid & 31, m0 + warp * 32, n0, M, d,
+                            bias, residual, out, act, res_first);
     } else {
 #pragma unroll 1
         for (int j0 = 0; j0 < BN; j0 += 32) {
@@ -429,12 +505,14 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Small-K variant (K <= 128: the 1x1 convs of OSNet, M up to 460 k pixels): memory/latency bound, so each CTA keeps
-// the whole weight matrix resident in smem, walks many 128-pixel tiles, double-buffers the A tile (cp.async for
-// tile t+1 is in flight while tile t is multiplied and written out) and double-buffers the accumulator in TMEM.
-// TMEM alloc / barrier init / weight loads are paid once per CTA instead of once per tile.
+// Small-K persistent variant (K <= 128: the 1x1 convs of OSNet, M up to 460 k pixels).  These layers are HBM/latency
+// bound, so the per-tile fixed costs are what matter.  Each CTA keeps the weight matrix resident in smem and walks
+// tiles blockIdx.x, +gridDim.x, ...; per tile `it` the steps overlap as
+//     cp.async gather of tile it+2  |  tcgen05.mma of tile it  |  epilogue (TMEM -> smem -> HBM) of tile it-1
+// with NBUF A buffers in smem and two accumulators in TMEM.  TMEM alloc, barrier init and the weight loads are paid
+// once per CTA.
 // ---------------------------------------------------------------------------------------------------------
-template <int BN, int NK>
+template <int BN, int NK, int NBUF>
 __global__ void __launch_bounds__(128) conv_tc_smallk_kernel(FmConvDesc d, const __half* __restrict__ in,
                                                               const __half* __restrict__ wgt,
                                                               const float* __restrict__ bias,
@@ -444,10 +522,11 @@ __global__ void __launch_bounds__(128) conv_tc_smallk_kernel(FmConvDesc d, const
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     constexpr int A_BYTES = TC_BM * 128, B_BYTES = BN * 128;
     uint8_t* sB = smem;                                  // NK slices of B
-    uint8_t* sA0 = smem + NK * B_BYTES;                  // 2 x NK slices of A
+    uint8_t* sA0 = smem + NK * B_BYTES;                  // NBUF x NK slices of A
+    uint8_t* sStg = sA0 + (size_t)NBUF * NK * A_BYTES;   // 4 warps x 32 rows x (BN*2+16) bytes
     __shared__ uint64_t bar_mma[2];
     __shared__ uint32_t s_tmem;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n0 = blockIdx.y * BN;
     const int M = d.n * d.ho * d.wo;
     const int Ktot = d.kh * d.kw * d.cin;
@@ -467,20 +546,37 @@ __global__ void __launch_bounds__(128) conv_tc_smallk_kernel(FmConvDesc d, const
     const uint32_t tmem_base = s_tmem;
     const int c = tid & 7, rbase = tid >> 3;
     const uint32_t idesc = make_idesc(BN);
+    const int n_my = (m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const bool pointwise = d.kh == 1 && d.kw == 1 && d.stride == 1 && d.pad == 0;
 
-    auto load_A = [&](int tile, int buf) {
-        const int m0 = tile * TC_BM;
+    auto load_A = [&](int i) {                           // i-th tile of this CTA -> buffer i % NBUF
+        if (i >= n_my) return;
+        const int m0 = (blockIdx.x + i * gridDim.x) * TC_BM;
+        const int buf = i % NBUF;
 #pragma unroll
         for (int ks = 0; ks < NK; ++ks) {
             uint8_t* sA = sA0 + (size_t)(buf * NK + ks) * A_BYTES;
             const int kelem = ks * TC_BK + c * 8;
             const bool kvalid = kelem < Ktot;
+            if (pointwise) {
+                const __half* base = in + d.cin_offset + (kvalid ? kelem : 0);
+#pragma unroll
+                for (int i2 = 0; i2 < 8; ++i2) {
+                    const int r = rbase + 16 * i2;
+                    const bool ok = kvalid && m0 + r < M;
+                    const __half* src = ok ? base + (size_t)(m0 + r) * d.cin_stride : in;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
+                                     smem_u32(sA + r * 128 + ((c ^ (r & 7)) << 4))),
+                                 "l"(src), "r"(ok ? 16u : 0u));
+                }
+                continue;
+            }
             const int tap = kvalid ? kelem / d.cin : 0;
             const int cch = kvalid ? kelem - tap * d.cin : 0;
             const int fr = tap / d.kw, fs = tap - fr * d.kw;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = rbase + 16 * i;
+            for (int i2 = 0; i2 < 8; ++i2) {
+                const int r = rbase + 16 * i2;
                 const int m = m0 + r;
                 const __half* src = in;
                 uint32_t bytes = 0;
@@ -498,7 +594,7 @@ __global__ void __launch_bounds__(128) conv_tc_smallk_kernel(FmConvDesc d, const
             }
         }
     };
-    // weights: resident for the whole CTA
+    // weights: resident for the whole CTA (same cp.async group as the first A tile)
 #pragma unroll
     for (int ks = 0; ks < NK; ++ks) {
         const int kelem = ks * TC_BK + c * 8;
@@ -513,47 +609,67 @@ __global__ void __launch_bounds__(128) conv_tc_smallk_kernel(FmConvDesc d, const
                          "l"(src), "r"(ok ? 16u : 0u));
         }
     }
-    int tile = blockIdx.x;
-    if (tile < m_tiles) load_A(tile, 0);
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    // prologue: NBUF-1 tiles in flight
+#pragma unroll
+    for (int i = 0; i < NBUF - 1; ++i) {
+        load_A(i);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     const int act = d.act & 0xff;
     const bool res_first = (d.act & FM_ACT_AFTER_RESIDUAL) != 0;
-    int it = 0;
-    for (; tile < m_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const int next = tile + gridDim.x;
-        if (next < m_tiles) load_A(next, buf ^ 1);     // buffer buf^1 was consumed by the MMAs of iteration it-1,
-        asm volatile("cp.async.commit_group;" ::: "memory");   // whose completion we waited for in that epilogue
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
+    const bool staged = staged_ok(d, residual);
+    uint8_t* stg = sStg + (size_t)warp * 32 * (BN * 2 + 16);
+
+    auto epilogue = [&](int j) {                         // accumulator j & 1 -> HBM (its MMAs are known complete)
+        const int m0 = (blockIdx.x + j * gridDim.x) * TC_BM;
+        const uint32_t lane_addr = tmem_base + (j & 1) * BN + ((uint32_t)(warp * 32) << 16);
+        if (staged) {
+            epilogue_staged<BN>(stg, lane_addr, lane, m0 + warp * 32, n0, M, d, bias, residual, out, act, res_first);
+        } else {
+            const int m = m0 + tid;
+#pragma unroll 1
+            for (int j0 = 0; j0 < BN; j0 += 32) {
+                float v32[32];
+                tmem_ld32(lane_addr + j0, v32);
+                if (m >= M) continue;
+                epilogue_store32(v32, (size_t)m, n0 + j0, d, bias, residual, out, act, res_first);
+            }
+        }
+    };
+
+    for (int it = 0; it < n_my; ++it) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(NBUF - 2) : "memory");   // tile `it` has landed (this thread)
         fence_async_smem();
+        tc_fence_before();       // orders the TMEM reads of epilogue(it-2) before the MMAs that reuse that accumulator
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
+            const int buf = it % NBUF;
 #pragma unroll
             for (int ks = 0; ks < NK; ++ks) {
                 const uint32_t a_addr = smem_u32(sA0 + (size_t)(buf * NK + ks) * A_BYTES);
                 const uint32_t b_addr = smem_u32(sB + (size_t)ks * B_BYTES);
 #pragma unroll
                 for (int k = 0; k < TC_BK / 16; ++k)
-                    mma_f16(tmem_base + buf * BN, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32),
+                    mma_f16(tmem_base + (it & 1) * BN, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32),
                             idesc, (ks > 0 || k > 0) ? 1u : 0u);
             }
-            tc_commit(&bar_mma[buf]);
+            tc_commit(&bar_mma[it & 1]);
         }
-        mbar_wait(&bar_mma[buf], (uint32_t)((it >> 1) & 1));
+        if (it > 0) {
+            // MMAs of tile it-1 done => its accumulator is readable and its A buffer ((it-1) % NBUF) is free
+            mbar_wait(&bar_mma[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) & 1));
+            tc_fence_after();
+        }
+        load_A(it + NBUF - 1);                           // lands in buffer (it-1) % NBUF
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (it > 0) epilogue(it - 1);
+    }
+    if (n_my > 0) {
+        const int j = n_my - 1;
+        mbar_wait(&bar_mma[j & 1], (uint32_t)((j >> 1) & 1));
         tc_fence_after();
-        // ---- epilogue of this tile (the next tile's copies are already in flight) ----
-        const int m = tile * TC_BM + tid;
-        const uint32_t lane_addr = tmem_base + buf * BN + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
-        for (int j0 = 0; j0 < BN; j0 += 32) {
-            float v32[32];
-            tmem_ld32(lane_addr + j0, v32);
-            if (m >= M) continue;
-            epilogue_store32(v32, (size_t)m, n0 + j0, d, bias, residual, out, act, res_first);
-        }
-        tc_fence_before();
-        __syncthreads();      // all TMEM reads of accumulator `buf` done before it is overwritten two tiles later
+        epilogue(j);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     tc_fence_before();
@@ -563,27 +679,28 @@ __global__ void __launch_bounds__(128) conv_tc_smallk_kernel(FmConvDesc d, const
                      "r"((uint32_t)(2 * BN < 32 ? 32 : 2 * BN)));
 }
 
-template <int BN, int NK>
+template <int BN, int NK, int NBUF>
 int launch_tc_smallk(const FmConvDesc* d, const void* in, const void* wgt, const float* bias, const void* residual,
                      void* out, cudaStream_t s) {
-    constexpr int smem = NK * BN * 128 + 2 * NK * TC_BM * 128 + 1024;
+    constexpr int smem = NK * BN * 128 + NBUF * NK * TC_BM * 128 + 4 * 32 * (BN * 2 + 16) + 1024;
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(conv_tc_smallk_kernel<BN, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(conv_tc_smallk_kernel<BN, NK, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr = true;
     }
     const int M = d->n * d->ho * d->wo;
     const int m_tiles = fm_cdiv(M, TC_BM);
     const int n_tiles = fm_cdiv(d->cout, BN);
-    int per_sm = (220 * 1024) / smem;                 // shared-memory limit
+    int per_sm = (226 * 1024) / (smem + 1024);        // shared-memory limit (1 KB per CTA is reserved by the driver)
     if (per_sm > 512 / (2 * BN)) per_sm = 512 / (2 * BN);   // TMEM limit: two BN-column accumulators per CTA
     if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
     int gx = FM_NUM_SMS * per_sm / n_tiles;
     if (gx < 1) gx = 1;
     if (gx > m_tiles) gx = m_tiles;
     dim3 grid(gx, n_tiles, 1);
-    conv_tc_smallk_kernel<BN, NK><<<grid, 128, smem, s>>>(*d, (const __half*)in, (const __half*)wgt, bias,
-                                                          (const __half*)residual, (__half*)out, m_tiles);
+    conv_tc_smallk_kernel<BN, NK, NBUF><<<grid, 128, smem, s>>>(*d, (const __half*)in, (const __half*)wgt, bias,
+                                                                (const __half*)residual, (__half*)out, m_tiles);
     return 0;
 }
 
@@ -682,10 +799,17 @@ extern "C" int fm_conv2d_tc(const FmConvDesc* d, const void* in, const void* wgt
         const char* e = getenv("FM_CONV_SMALLK");
         smallk_mode = (e && e[0] == '1') ? 1 : 0;   // measured slower than the tile-per-CTA kernel: off by default
     }
-    if (smallk_mode && nk <= 2 && m_tiles_all >= 2 * FM_NUM_SMS) {      // big-M, tiny-K: persistent variant
-        if (d->cout <= 32) { if (nk == 1) launch_tc_smallk<32, 1>(d, in, wgt, bias, residual, out, s); else launch_tc_smallk<32, 2>(d, in, wgt, bias, residual, out, s); }
-        else if (d->cout <= 64) { if (nk == 1) launch_tc_smallk<64, 1>(d, in, wgt, bias, residual, out, s); else launch_tc_smallk<64, 2>(d, in, wgt, bias, residual, out, s); }
-        else { if (nk == 1) launch_tc_smallk<128, 1>(d, in, wgt, bias, residual, out, s); else launch_tc_smallk<128, 2>(d, in, wgt, bias, residual, out, s); }
+    if (smallk_mode && nk <= 2 && m_tiles_all >= 4 * FM_NUM_SMS) {      // big-M, tiny-K: persistent variant
+        if (d->cout <= 32) {
+            if (nk == 1) launch_tc_smallk<32, 1, 3>(d, in, wgt, bias, residual, out, s);
+            else launch_tc_smallk<32, 2, 3>(d, in, wgt, bias, residual, out, s);
+        } else if (d->cout <= 64) {
+            if (nk == 1) launch_tc_smallk<64, 1, 3>(d, in, wgt, bias, residual, out, s);
+            else launch_tc_smallk<64, 2, 3>(d, in, wgt, bias, residual, out, s);
+        } else {
+            if (nk == 1) launch_tc_smallk<128, 1, 3>(d, in, wgt, bias, residual, out, s);
+            else launch_tc_smallk<128, 2, 3>(d, in, wgt, bias, residual, out, s);
+        }
         FM_CHECK_LAUNCH("fm_conv2d_tc(smallk)");
         return FM_OK;
     }

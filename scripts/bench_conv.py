@@ -19,6 +19,9 @@ SHAPES = [  # n, h, w, cin, cout, k, stride
     (1, 80, 80, 128, 256, 3, 1), (1, 40, 40, 256, 512, 3, 1), (1, 20, 20, 512, 1024, 3, 1), (1, 160, 160, 64, 64, 3, 1),
     (1, 320, 320, 32, 64, 3, 2), (1, 640, 640, 8, 32, 3, 1),
 ]
+ONLY = [int(a.split('=')[1]) for a in sys.argv if a.startswith('--only=')]
+if ONLY:
+    SHAPES = [SHAPES[i] for i in ONLY]
 for (n, h, w, cin, cout, k, st) in SHAPES:
     pad = k // 2
     ho, wo = (h + 2 * pad - k) // st + 1, (w + 2 * pad - k) // st + 1

@@ -86,7 +86,7 @@ def test_conv_simt_vs_torch(case):
     (1, 10, 10, 640, 24, 1, 1, 'logistic', 640, 0, 24, 0, False),     # split-K, ragged cout
     (40, 64, 32, 64, 64, 1, 1, 'linear', 64, 0, 64, 0, False),        # persistent small-K variant (640 tiles)
     (40, 64, 32, 64, 256, 1, 1, 'relu', 64, 0, 256, 0, True),         # small-K, 2 N tiles, residual
-    (24, 64, 32, 96, 96, 1, 1, 'relu', 96, 0, 96, 0, False),          # small-K with 2 K slices (K = 96)
+    (40, 64, 32, 96, 96, 1, 1, 'relu', 96, 0, 96, 0, False),          # small-K with 2 K slices (K = 96)
     (40, 64, 32, 128, 24, 1, 1, 'linear', 128, 0, 24, 0, False),      # small-K, ragged cout, BN = 32
 ])
 def test_conv_tc_vs_torch(case):
