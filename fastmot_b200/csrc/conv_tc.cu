@@ -710,13 +710,53 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(FmConvDesc d, const 
                                                              __half* __restrict__ out) {
     const int M = d.n * d.ho * d.wo;
     const size_t total = (size_t)M * d.cout;
+    const int act = d.act & 0xff;
+    const bool res_first = (d.act & FM_ACT_AFTER_RESIDUAL) != 0;
+    if (staged_ok(d, residual)) {
+        // 8 channels per thread: two 128-bit partial-sum loads per split, one 128-bit store
+        const int cg = d.cout >> 3;
+        const size_t total8 = (size_t)M * cg;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8;
+             i += (size_t)gridDim.x * blockDim.x) {
+            const size_t m = i / cg;
+            const int n = (int)(i - m * cg) * 8;
+            float x[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) x[q] = bias ? bias[n + q] : 0.f;
+            const float* wp = ws + m * d.cout + n;
+            for (int z = 0; z < splits; ++z) {
+                const float4 a = *reinterpret_cast<const float4*>(wp + (size_t)z * total);
+                const float4 b2 = *reinterpret_cast<const float4*>(wp + (size_t)z * total + 4);
+                x[0] += a.x; x[1] += a.y; x[2] += a.z; x[3] += a.w;
+                x[4] += b2.x; x[5] += b2.y; x[6] += b2.z; x[7] += b2.w;
+            }
+            if (!res_first) tc_act8(x, act);
+            if (residual) {
+                const uint4 rv = *reinterpret_cast<const uint4*>(residual + m * d.res_stride + d.res_offset + n);
+                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 f = __half22float2(rh[q]);
+                    x[2 * q] += f.x;
+                    x[2 * q + 1] += f.y;
+                }
+            }
+            if (res_first) tc_act8(x, act);
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const __half2 h = __floats2half2_rn(x[2 * q], x[2 * q + 1]);
+                w[q] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(out + m * d.cout_stride + d.cout_offset + n) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        return;
+    }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t m = i / d.cout;
         const int n = (int)(i - m * d.cout);
         float acc = 0.f;
         for (int z = 0; z < splits; ++z) acc += ws[(size_t)z * total + i];
-        const int act = d.act & 0xff;
-        const bool res_first = (d.act & FM_ACT_AFTER_RESIDUAL) != 0;
         float v = acc + (bias ? bias[n] : 0.f);
         if (!res_first) v = tc_act(v, act);
         if (residual) v += __half2float(residual[m * d.res_stride + d.res_offset + n]);
@@ -818,6 +858,12 @@ extern "C" int fm_conv2d_tc(const FmConvDesc* d, const void* in, const void* wgt
     static int force_bn = -1;      // FM_CONV_BN=32|64|128 overrides the tile width (experiments only)
     if (force_bn < 0) { const char* e = getenv("FM_CONV_BN"); force_bn = e ? atoi(e) : 0; }
     int bn = d->cout <= 32 ? 32 : d->cout <= 64 ? 64 : 128;
+    if (bn == 128) {
+        // between half a wave and two waves of 128-wide tiles, 64-wide tiles fill the 148 SMs better (measured on
+        // 128->128 @ 224x16x8 and the 80x80 YOLO 3x3); fewer tiles than that go to split-K instead
+        const int tiles128 = m_tiles_all * ((d->cout + 127) / 128);
+        if (tiles128 > FM_NUM_SMS / 2 && tiles128 < 2 * FM_NUM_SMS) bn = 64;
+    }
     if (force_bn) bn = force_bn;
     if (bn == 32) {
         if (nk == 1) launch_tc<32, 1>(d, in, wgt, bias, residual, out, s);

@@ -282,6 +282,62 @@ __global__ void __launch_bounds__(256) fc_norm_kernel(const float* __restrict__ 
     for (int j = threadIdx.x; j < cout; j += blockDim.x) out[(size_t)b * cout + j] *= inv;
 }
 
+// Same op, S samples per CTA and one warp per output feature: lanes stride the weight row with 128-bit loads
+// (coalesced; the row-per-thread kernel above reads 32 different rows per load instruction), the weight row is
+// reused for the S samples, and the L2 norm is taken from shared memory before a single coalesced store.
+template <int S>
+__global__ void __launch_bounds__(256) fc_norm_warp_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, float* __restrict__ out,
+                                                            int n, int cin, int cout, int relu, int normalize) {
+    extern __shared__ float fsm[];   // x[S][cin] | y[S][cout]
+    __shared__ float s_inv[S];
+    float* sx = fsm;
+    float* sy = fsm + (size_t)S * cin;
+    const int b0 = blockIdx.x * S;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < S * cin; i += blockDim.x) {
+        const int s = i / cin, b = b0 + s;
+        sx[i] = b < n ? in[(size_t)b * cin + (i - s * cin)] : 0.f;
+    }
+    __syncthreads();
+    const int c4 = cin >> 2;
+    for (int j = warp; j < cout; j += 8) {
+        const float4* wr = reinterpret_cast<const float4*>(w + (size_t)j * cin);
+        float acc[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) acc[s] = 0.f;
+        for (int i = lane; i < c4; i += 32) {
+            const float4 wv = wr[i];
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                const float4 xv = reinterpret_cast<const float4*>(sx + (size_t)s * cin)[i];
+                acc[s] += wv.x * xv.x + wv.y * xv.y + wv.z * xv.z + wv.w * xv.w;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            float a = warp_sum(acc[s]);
+            if (lane == 0) {
+                a += bias ? bias[j] : 0.f;
+                if (relu) a = fmaxf(a, 0.f);
+                sy[(size_t)s * cout + j] = a;
+            }
+        }
+    }
+    __syncthreads();
+    if (warp < S) {
+        float sq = 0.f;
+        for (int j = lane; j < cout; j += 32) { const float a = sy[(size_t)warp * cout + j]; sq += a * a; }
+        sq = warp_sum(sq);
+        if (lane == 0) s_inv[warp] = normalize ? 1.f / sqrtf(sq) : 1.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < S * cout; i += blockDim.x) {
+        const int s = i / cout, b = b0 + s;
+        if (b < n) out[(size_t)b * cout + (i - s * cout)] = sy[i] * s_inv[s];
+    }
+}
+
 // strided variant: operands are channel slices of wider NHWC buffers
 __global__ void add_act_strided_kernel(const __half* __restrict__ a, int a_stride, int a_off,
                                        const __half* __restrict__ b, int b_stride, int b_off, __half* __restrict__ out,
@@ -420,6 +476,14 @@ extern "C" int fm_channel_gate(const void* x, float* pooled, float* gate, const 
 extern "C" int fm_fc_norm(const float* in, const float* w, const float* bias, float* out, int n, int cin, int cout,
                           int relu, int normalize, void* stream) {
     if (n <= 0) return FM_OK;
+    if ((cin & 3) == 0 && cin <= 4096 && cout <= 4096) {
+        constexpr int S = 2;
+        const size_t smem = (size_t)S * (cin + cout) * sizeof(float);
+        fc_norm_warp_kernel<S><<<(n + S - 1) / S, 256, smem, (cudaStream_t)stream>>>(in, w, bias, out, n, cin, cout,
+                                                                                    relu, normalize);
+        FM_CHECK_LAUNCH("fm_fc_norm");
+        return FM_OK;
+    }
     fc_norm_kernel<<<n, 256, (cin + 8) * sizeof(float), (cudaStream_t)stream>>>(in, w, bias, out, cin, cout, relu,
                                                                                normalize);
     FM_CHECK_LAUNCH("fm_fc_norm");

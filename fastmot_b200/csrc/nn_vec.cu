@@ -6,19 +6,30 @@
 
 namespace {
 
-struct H8 { __half2 v[4]; };
+// 8 halves moved as ONE 128-bit access.  (A struct of four __half2 is copied member-wise by nvcc -- four 32-bit
+// LDG/STG per vector -- so the payload is a uint4 and the half2 view is taken only for arithmetic.)
+struct H8 { uint4 u; };
 static_assert(sizeof(H8) == 16, "H8 must be 16 bytes");
 
-__device__ __forceinline__ H8 ld8(const __half* p) { return *reinterpret_cast<const H8*>(p); }
-__device__ __forceinline__ void st8(__half* p, const H8& v) { *reinterpret_cast<H8*>(p) = v; }
+__device__ __forceinline__ H8 ld8(const __half* p) { H8 h; h.u = *reinterpret_cast<const uint4*>(p); return h; }
+__device__ __forceinline__ void st8(__half* p, const H8& v) { *reinterpret_cast<uint4*>(p) = v.u; }
+__device__ __forceinline__ float2 h2f(uint32_t w) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
+__device__ __forceinline__ uint32_t f2h(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
 __device__ __forceinline__ void to_f(const H8& h, float* f) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { float2 t = __half22float2(h.v[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+    float2 t;
+    t = h2f(h.u.x); f[0] = t.x; f[1] = t.y;
+    t = h2f(h.u.y); f[2] = t.x; f[3] = t.y;
+    t = h2f(h.u.z); f[4] = t.x; f[5] = t.y;
+    t = h2f(h.u.w); f[6] = t.x; f[7] = t.y;
 }
 __device__ __forceinline__ H8 to_h(const float* f) {
     H8 h;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) h.v[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    h.u = make_uint4(f2h(f[0], f[1]), f2h(f[2], f[3]), f2h(f[4], f[5]), f2h(f[6], f[7]));
     return h;
 }
 
@@ -70,7 +81,9 @@ __global__ void __launch_bounds__(256) dwconv3_vec(const __half* __restrict__ in
 }
 
 // depthwise 3x3: 4 horizontally adjacent pixels x 8 channels per thread (weights and the 3x6 input window are loaded
-// once per thread: 18 + 9 vector loads for 4 outputs instead of 4 x 18)
+// once per thread: 18 + 9 vector loads for 4 outputs instead of 4 x 18).  Border taps read a clamped (valid) address
+// and are zeroed afterwards, so the six loads of a row carry no control dependence and issue back to back; the
+// earlier `continue`-guarded version exposed one DRAM latency per load (measured 4.8x off the HBM roofline).
 __global__ void __launch_bounds__(256) dwconv3_vec4(const __half* __restrict__ in, const __half* __restrict__ w,
                                                      const float* __restrict__ bias, __half* __restrict__ out, int n,
                                                      int h, int wd, int c, int act) {
@@ -82,25 +95,40 @@ __global__ void __launch_bounds__(256) dwconv3_vec4(const __half* __restrict__ i
         const int x0 = (int)(t % xg) * 4; t /= xg;
         const int y = t % h;
         const int b = t / h;
+        // all 18 window loads first (clamped addresses), weights next, math last
+        H8 raw[3][6];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int yy = min(max(y + r - 1, 0), h - 1);
+            const __half* row = in + (((size_t)b * h + yy) * wd) * c + g * 8;
+#pragma unroll
+            for (int cx = 0; cx < 6; ++cx) {
+                const int xx = min(max(x0 + cx - 1, 0), wd - 1);
+                raw[r][cx] = ld8(row + (size_t)xx * c);
+            }
+        }
         float acc[4][8];
 #pragma unroll
-        for (int p = 0; p < 4; ++p)
+        for (int q = 0; q < 8; ++q) {
+            const float bq = bias ? bias[g * 8 + q] : 0.f;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) acc[p][q] = bias ? bias[g * 8 + q] : 0.f;
+            for (int p = 0; p < 4; ++p) acc[p][q] = bq;
+        }
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             const int yy = y + r - 1;
-            if (yy < 0 || yy >= h) continue;
-            const __half* row = in + (((size_t)b * h + yy) * wd) * c + g * 8;
+            const bool rok = yy >= 0 && yy < h;
             float ww[3][8];
 #pragma unroll
             for (int k = 0; k < 3; ++k) to_f(ld8(w + (size_t)(r * 3 + k) * c + g * 8), ww[k]);
 #pragma unroll
             for (int cx = 0; cx < 6; ++cx) {
                 const int xx = x0 + cx - 1;
-                if (xx < 0 || xx >= wd) continue;
+                const bool ok = rok && xx >= 0 && xx < wd;
+                H8 v = raw[r][cx];
+                if (!ok) v.u = make_uint4(0u, 0u, 0u, 0u);
                 float a[8];
-                to_f(ld8(row + (size_t)xx * c), a);
+                to_f(v, a);
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
                     const int s = cx - p;          // tap column for output pixel p

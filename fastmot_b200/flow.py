@@ -129,6 +129,9 @@ class Flow:
         self._h_flags = torch.zeros(32, dtype=i32).pin_memory()
         self._h_slots = torch.zeros(max_tracks, dtype=i32).pin_memory()
         self._uploader = FrameUploader(size)
+        self._side = torch.cuda.Stream()
+        self._ev_lk = torch.cuda.Event()
+        self._ev_h = torch.cuda.Event()
         self.pool = None
         self._order = []
         self._bg_cache = None
@@ -223,18 +226,26 @@ class Flow:
                                    float(crit[2]), 1e-4, float(self.max_error), ptr(self.all_cur), ptr(self.status),
                                    ptr(self.err), s), "fm_lk_track")
         self.prev = cur   # flow.py:212-213
+        # camera-motion RANSAC (one CTA, latency bound) runs on a side stream next to the per-track affine rounds:
+        # they only share read-only LK outputs.  The affine kernels no longer gate on h_ok -- when the homography
+        # fails the caller drops every KLT box anyway (flow.py:227-229, tracker.py:152-156).
+        main = torch.cuda.current_stream()
+        self._ev_lk.record(main)
+        self._side.wait_event(self._ev_lk)
+        s_h = C.c_void_p(self._side.cuda_stream)
         _lib.check(lib.fm_ransac_homography(ptr(self.all_prev), ptr(self.all_cur), ptr(self.status), ptr(self.meta),
                                             int(self.ransac_max_iter), float(self.ransac_conf), 3.0,
                                             int(self.inlier_thresh), ptr(self.good_idx), ptr(self.inl_idx),
                                             ptr(h_dev), ptr(h_ok_dev), ptr(self.bg_kp), ptr(self.bg_kp_prev),
-                                            ptr(self.bg_kp_count), self.max_bg, s), "fm_ransac_homography")
+                                            ptr(self.bg_kp_count), self.max_bg, s_h), "fm_ransac_homography")
+        self._ev_h.record(self._side)
         self._bg_cache = None
         rounds = 0
         while True:
             step = 2
             _lib.check(lib.fm_ransac_affine_partial_batch(
                 ptr(self.all_prev), ptr(self.all_cur), ptr(self.status), ptr(self.trk_begin), ptr(self.slots_dev), n,
-                step, C.c_void_p(fl + 32), ptr(h_ok_dev), ptr(self.est_boxes), ptr(self.sig), ptr(pool.tlbr),
+                step, C.c_void_p(fl + 32), None, ptr(self.est_boxes), ptr(self.sig), ptr(pool.tlbr),
                 ptr(pool.klt_tlbr), ptr(pool.klt_ok), ptr(pool.inlier_ratio), ptr(pool.kp), ptr(pool.kp_prev),
                 ptr(pool.kp_count), pool.max_kp, W, H, int(self.ransac_max_iter), float(self.ransac_conf), 3.0,
                 int(self.inlier_thresh), 10, rounds, s), "fm_ransac_affine_partial_batch")
@@ -247,6 +258,7 @@ class Flow:
             if n == 0 or hf[8 + ((rounds - 1) & 15)] == 0 or rounds >= 2 * max(n, 1) + 2:
                 break
         self.rounds_last = rounds
+        main.wait_event(self._ev_h)          # H / h_ok are consumed by the Kalman step that follows
         return self._order
 
     def fetch_klt_bboxes(self, order=None):
