@@ -29,13 +29,20 @@ __device__ __forceinline__ float group_sum(float v) {
 
 // Sum of the per-lane row arrays in OpenCV's sequential row-major order (bit-exact fp32 accumulation):
 // lane r continues the running sum handed over by lane r-1.
-template <int NQ>
-__device__ __forceinline__ void group_seq_sum(float (*vals)[LK_MAX_WIN], int win_w, int win_h, int lane8, float* out) {
+// WW / WH: compile-time window size (0 = use the runtime win_w / win_h); the reference always runs 5x5, and with
+// constant bounds the per-element predicates and loop overhead disappear (the profile had them at ~19 % of the
+// kernel's instructions).
+template <int NQ, int WW, int WH>
+__device__ __forceinline__ void group_seq_sum(float (*vals)[LK_MAX_WIN], int win_w_rt, int win_h_rt, int lane8,
+                                              float* out) {
+    const int win_w = WW ? WW : win_w_rt, win_h = WH ? WH : win_h_rt;
     const int lane = threadIdx.x & 31, gbase = lane & ~7;
     float acc[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) acc[q] = 0.f;
-    for (int r = 0; r < win_h; ++r) {
+#pragma unroll
+    for (int r = 0; r < (WH ? WH : LK_MAX_WIN); ++r) {
+        if (r >= win_h) break;
         float in[NQ];
 #pragma unroll
         for (int q = 0; q < NQ; ++q) in[q] = __shfl_sync(0xffffffffu, acc[q], gbase | (r > 0 ? r - 1 : 0));
@@ -63,12 +70,67 @@ __device__ __forceinline__ short2 dv(const short2* d, int w, int h, int x, int y
     return d[(size_t)y * w + x];
 }
 
+// Rows y and y+1, columns x0 .. x0+ww of an 8-bit level (BORDER_REFLECT_101 outside).  The bilinear taps of
+// neighbouring window columns share pixels, so a lane fetches 2 x (ww+1) values once instead of 4 per column, and
+// windows that lie inside the image (nearly all of them) skip the reflection arithmetic, which was > 50 % of the
+// kernel's executed instructions.
+template <int WW>
+__device__ __forceinline__ void fetch_px_rows(const unsigned char* __restrict__ img, int W, int H, int x0, int y,
+                                              int win_w_rt, int* r0, int* r1) {
+    const int ww = WW ? WW : win_w_rt;
+    if (x0 >= 0 && x0 + ww < W && y >= 0 && y + 1 < H) {
+        const unsigned char* p = img + (size_t)y * W + x0;
+#pragma unroll
+        for (int x = 0; x <= (WW ? WW : LK_MAX_WIN); ++x) {
+            if (x > ww) break;
+            r0[x] = p[x];
+            r1[x] = p[W + x];
+        }
+    } else {
+        const unsigned char* pa = img + (size_t)refl101(y, H) * W;
+        const unsigned char* pb = img + (size_t)refl101(y + 1, H) * W;
+#pragma unroll
+        for (int x = 0; x <= (WW ? WW : LK_MAX_WIN); ++x) {
+            if (x > ww) break;
+            const int xr = refl101(x0 + x, W);
+            r0[x] = pa[xr];
+            r1[x] = pb[xr];
+        }
+    }
+}
+
+// same for the int16 Scharr derivative level (BORDER_CONSTANT 0 outside)
+template <int WW>
+__device__ __forceinline__ void fetch_dv_rows(const short2* __restrict__ d, int W, int H, int x0, int y, int win_w_rt,
+                                              short2* d0, short2* d1) {
+    const int ww = WW ? WW : win_w_rt;
+    if (x0 >= 0 && x0 + ww < W && y >= 0 && y + 1 < H) {
+        const short2* p = d + (size_t)y * W + x0;
+#pragma unroll
+        for (int x = 0; x <= (WW ? WW : LK_MAX_WIN); ++x) {
+            if (x > ww) break;
+            d0[x] = p[x];
+            d1[x] = p[W + x];
+        }
+    } else {
+#pragma unroll
+        for (int x = 0; x <= (WW ? WW : LK_MAX_WIN); ++x) {
+            if (x > ww) break;
+            d0[x] = dv(d, W, H, x0 + x, y);
+            d1[x] = dv(d, W, H, x0 + x, y + 1);
+        }
+    }
+}
+
+template <int WW, int WH>
 __global__ void __launch_bounds__(128) lk_kernel(FmPyramid prev, FmPyramid cur, const float* __restrict__ pts_full,
                                                   const int* __restrict__ meta, float pt_scale_x, float pt_scale_y,
-                                                  int win_w, int win_h, int max_count, double eps_sq, float min_eig_thr,
+                                                  int win_w_rt, int win_h_rt, int max_count, double eps_sq,
+                                                  float min_eig_thr,
                                                   float max_error, float unscale_x, float unscale_y,
                                                   float* __restrict__ out_pts, unsigned char* __restrict__ out_status,
                                                   float* __restrict__ out_err) {
+    const int win_w = WW ? WW : win_w_rt, win_h = WH ? WH : win_h_rt;
     const int n_pts = meta[1];
     const int lane8 = threadIdx.x & 7;
     const int groups_per_block = blockDim.x >> 3;
@@ -110,15 +172,17 @@ __global__ void __launch_bounds__(128) lk_kernel(FmPyramid prev, FmPyramid cur, 
             for (int x = 0; x < LK_MAX_WIN; ++x) { pa[0][x] = 0.f; pa[1][x] = 0.f; pa[2][x] = 0.f; }
             if (lvl_on && row_on) {
                 const int y = iy + lane8;
+                int r0[LK_MAX_WIN + 1], r1[LK_MAX_WIN + 1];
+                short2 e0[LK_MAX_WIN + 1], e1[LK_MAX_WIN + 1];
+                fetch_px_rows<WW>(I, W, H, ix, y, win_w, r0, r1);
+                fetch_dv_rows<WW>(dI, W, H, ix, y, win_w, e0, e1);
 #pragma unroll
-                for (int x = 0; x < LK_MAX_WIN; ++x) {
+                for (int x = 0; x < (WW ? WW : LK_MAX_WIN); ++x) {
                     if (x >= win_w) break;
-                    const int xx = ix + x;
-                    const int ival = (px(I, W, H, xx, y) * iw00 + px(I, W, H, xx + 1, y) * iw01 +
-                                      px(I, W, H, xx, y + 1) * iw10 + px(I, W, H, xx + 1, y + 1) * iw11 +
+                    const int ival = (r0[x] * iw00 + r0[x + 1] * iw01 + r1[x] * iw10 + r1[x + 1] * iw11 +
                                       (1 << (LK_W_BITS - 5 - 1))) >> (LK_W_BITS - 5);
-                    const short2 d00 = dv(dI, W, H, xx, y), d01 = dv(dI, W, H, xx + 1, y);
-                    const short2 d10 = dv(dI, W, H, xx, y + 1), d11 = dv(dI, W, H, xx + 1, y + 1);
+                    const short2 d00 = e0[x], d01 = e0[x + 1];
+                    const short2 d10 = e1[x], d11 = e1[x + 1];
                     const int ixv = (d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11 +
                                      (1 << (LK_W_BITS - 1))) >> LK_W_BITS;
                     const int iyv = (d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11 +
@@ -128,7 +192,7 @@ __global__ void __launch_bounds__(128) lk_kernel(FmPyramid prev, FmPyramid cur, 
                 }
             }
             float asum[3];
-            group_seq_sum<3>(pa, win_w, win_h, lane8, asum);
+            group_seq_sum<3, WW, WH>(pa, win_w, win_h, lane8, asum);
             float A11 = asum[0], A12 = asum[1], A22 = asum[2];
             const float FLT_SCALE = 1.f / (1 << 20);
             A11 *= FLT_SCALE; A12 *= FLT_SCALE; A22 *= FLT_SCALE;
@@ -160,12 +224,12 @@ __global__ void __launch_bounds__(128) lk_kernel(FmPyramid prev, FmPyramid cur, 
                 for (int x = 0; x < LK_MAX_WIN; ++x) { pb[0][x] = 0.f; pb[1][x] = 0.f; }
                 if (iter_on && row_on) {
                     const int y = jy + lane8;
+                    int r0[LK_MAX_WIN + 1], r1[LK_MAX_WIN + 1];
+                    fetch_px_rows<WW>(J, W, H, jx, y, win_w, r0, r1);
 #pragma unroll
-                    for (int x = 0; x < LK_MAX_WIN; ++x) {
+                    for (int x = 0; x < (WW ? WW : LK_MAX_WIN); ++x) {
                         if (x >= win_w) break;
-                        const int xx = jx + x;
-                        const int jval = (px(J, W, H, xx, y) * jw00 + px(J, W, H, xx + 1, y) * jw01 +
-                                          px(J, W, H, xx, y + 1) * jw10 + px(J, W, H, xx + 1, y + 1) * jw11 +
+                        const int jval = (r0[x] * jw00 + r0[x + 1] * jw01 + r1[x] * jw10 + r1[x + 1] * jw11 +
                                           (1 << (LK_W_BITS - 5 - 1))) >> (LK_W_BITS - 5);
                         const int diff = jval - Iv[x];
                         pb[0][x] = (float)(diff * Ix[x]);
@@ -173,7 +237,7 @@ __global__ void __launch_bounds__(128) lk_kernel(FmPyramid prev, FmPyramid cur, 
                     }
                 }
                 float bsum[2];
-                group_seq_sum<2>(pb, win_w, win_h, lane8, bsum);
+                group_seq_sum<2, WW, WH>(pb, win_w, win_h, lane8, bsum);
                 const float b1 = bsum[0] * FLT_SCALE, b2s = bsum[1] * FLT_SCALE;
                 if (iter_on) {
                     const float dx = (A12 * b2s - A22 * b1) * D, dy = (A12 * b1 - A11 * b2s) * D;
@@ -202,12 +266,12 @@ __global__ void __launch_bounds__(128) lk_kernel(FmPyramid prev, FmPyramid cur, 
                 float ev = 0.f;
                 if (err_on && row_on) {
                     const int y = jy + lane8;
+                    int r0[LK_MAX_WIN + 1], r1[LK_MAX_WIN + 1];
+                    fetch_px_rows<WW>(J, W, H, jx, y, win_w, r0, r1);
 #pragma unroll
-                    for (int x = 0; x < LK_MAX_WIN; ++x) {
+                    for (int x = 0; x < (WW ? WW : LK_MAX_WIN); ++x) {
                         if (x >= win_w) break;
-                        const int xx = jx + x;
-                        const int jval = (px(J, W, H, xx, y) * jw00 + px(J, W, H, xx + 1, y) * jw01 +
-                                          px(J, W, H, xx, y + 1) * jw10 + px(J, W, H, xx + 1, y + 1) * jw11 +
+                        const int jval = (r0[x] * jw00 + r0[x + 1] * jw01 + r1[x] * jw10 + r1[x + 1] * jw11 +
                                           (1 << (LK_W_BITS - 5 - 1))) >> (LK_W_BITS - 5);
                         ev += (float)abs(jval - Iv[x]);
                     }
@@ -239,10 +303,14 @@ extern "C" int fm_lk_track(const FmPyramid* prev, const FmPyramid* cur, const fl
     // OpenCV clamps the criteria: maxCount in [0,100], epsilon in [0,10], then squares epsilon
     max_count = max_count < 0 ? 0 : (max_count > 100 ? 100 : max_count);
     double e = epsilon < 0 ? 0 : (epsilon > 10 ? 10 : epsilon);
-    lk_kernel<<<FM_NUM_SMS * 8, 128, 0, (cudaStream_t)stream>>>(*prev, *cur, pts_full, meta, pt_scale_x, pt_scale_y,
-                                                                win_w, win_h, max_count, e * e, min_eig_thr,
-                                                                max_error, 1.0f / pt_scale_x, 1.0f / pt_scale_y,
-                                                                out_pts, out_status, out_err);
+    if (win_w == 5 && win_h == 5)       // the reference's (only) configuration: compile-time window
+        lk_kernel<5, 5><<<FM_NUM_SMS * 8, 128, 0, (cudaStream_t)stream>>>(
+            *prev, *cur, pts_full, meta, pt_scale_x, pt_scale_y, win_w, win_h, max_count, e * e, min_eig_thr, max_error,
+            1.0f / pt_scale_x, 1.0f / pt_scale_y, out_pts, out_status, out_err);
+    else
+        lk_kernel<0, 0><<<FM_NUM_SMS * 8, 128, 0, (cudaStream_t)stream>>>(
+            *prev, *cur, pts_full, meta, pt_scale_x, pt_scale_y, win_w, win_h, max_count, e * e, min_eig_thr, max_error,
+            1.0f / pt_scale_x, 1.0f / pt_scale_y, out_pts, out_status, out_err);
     FM_CHECK_LAUNCH("fm_lk_track");
     return FM_OK;
 }
