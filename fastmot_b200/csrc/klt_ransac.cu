@@ -39,7 +39,7 @@ __device__ int ransac_update_num_iters(double p, double ep, int model_points, in
 
 // ------------------------------------------------------------------------------------------------ block reduce
 template <int N>
-__device__ void block_reduce(double* vals, double* s_red /* [nwarps][N] */, double* s_out /* [N] */) {
+__device__ __forceinline__ void block_reduce(double* vals, double* s_red /* [nwarps][N] */, double* s_out /* [N] */) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
@@ -87,7 +87,7 @@ __device__ bool solve_dense(double* A, double* b, int n) {
 // Problem concept: static const int NP; void accumulate(const double* x, bool need_jac, double* acc) where
 // acc = [S, v[NP], A upper-triangular row-major NP(NP+1)/2]; block-parallel, result reduced into s_acc.
 template <class Problem>
-__device__ void lm_refine(Problem& prob, double* x /* shared [NP] */, int max_iters, double* s_red, double* s_acc,
+__device__ __forceinline__ void lm_refine(Problem& prob, double* x /* shared [NP] */, int max_iters, double* s_red, double* s_acc,
                           double* s_work /* >= 3*NP*NP + 6*NP doubles */) {
     constexpr int NP = Problem::NP;
     constexpr int NA = 1 + NP + NP * (NP + 1) / 2;
@@ -123,7 +123,7 @@ __device__ void lm_refine(Problem& prob, double* x /* shared [NP] */, int max_it
         }
         __syncthreads();
         prob.accumulate(xd, false, acc);
-        block_reduce<NA>(acc, s_red, s_acc);
+        block_reduce<1>(acc, s_red, s_acc);      // only the residual norm is needed for the trial step
         const bool improved = s_acc[0] < s_S;
         if (threadIdx.x == 0) {
             const double Sd = s_acc[0], S = s_S;
@@ -190,8 +190,9 @@ struct AffineProblem {
     const float* dst;
     const int* idx;  // inlier index list
     int n;
-    __device__ void accumulate(const double* h, bool need_jac, double* acc) const {
+    __device__ __forceinline__ void accumulate(const double* h, bool need_jac, double* acc) const {
         constexpr int NA = 1 + 4 + 10;
+#pragma unroll
         for (int k = 0; k < NA; ++k) acc[k] = 0.0;
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             const int p = idx[i];
@@ -202,8 +203,10 @@ struct AffineProblem {
             if (need_jac) {
                 const double J0[4] = {Mx, -My, 1.0, 0.0}, J1[4] = {My, Mx, 0.0, 1.0};
                 int q = 5;
+#pragma unroll
                 for (int a = 0; a < 4; ++a) {
                     acc[1 + a] += J0[a] * ex + J1[a] * ey;
+#pragma unroll
                     for (int b = a; b < 4; ++b) acc[q++] += J0[a] * J0[b] + J1[a] * J1[b];
                 }
             }
@@ -217,23 +220,31 @@ struct HomographyProblem {
     const float* dst;
     const int* idx;
     int n;
-    __device__ void accumulate(const double* h, bool need_jac, double* acc) const {
+    const float4* cache;   // optional shared-memory copy of the n inlier pairs (src.x, src.y, dst.x, dst.y)
+    __device__ __forceinline__ void accumulate(const double* h, bool need_jac, double* acc) const {
         constexpr int NA = 1 + 8 + 36;
+#pragma unroll
         for (int k = 0; k < NA; ++k) acc[k] = 0.0;
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const int p = idx[i];
-            const double Mx = src[2 * p], My = src[2 * p + 1];
+            // every LM pass re-reads all pairs: from the cache when they fit (two dependent L2 round trips per pass
+            // were ~60 % of the kernel's stall samples)
+            float4 pr;
+            if (cache) pr = cache[i];
+            else { const int p = idx[i]; pr = make_float4(src[2 * p], src[2 * p + 1], dst[2 * p], dst[2 * p + 1]); }
+            const double Mx = pr.x, My = pr.y;
             double ww = h[6] * Mx + h[7] * My + 1.0;
             ww = fabs(ww) > DBL_EPSILON ? 1.0 / ww : 0.0;
             const double xi = (h[0] * Mx + h[1] * My + h[2]) * ww, yi = (h[3] * Mx + h[4] * My + h[5]) * ww;
-            const double ex = xi - dst[2 * p], ey = yi - dst[2 * p + 1];
+            const double ex = xi - pr.z, ey = yi - pr.w;
             acc[0] += ex * ex + ey * ey;
             if (need_jac) {
                 const double J0[8] = {Mx * ww, My * ww, ww, 0, 0, 0, -Mx * ww * xi, -My * ww * xi};
                 const double J1[8] = {0, 0, 0, Mx * ww, My * ww, ww, -Mx * ww * yi, -My * ww * yi};
                 int q = 9;
+#pragma unroll
                 for (int a = 0; a < 8; ++a) {
                     acc[1 + a] += J0[a] * ex + J1[a] * ey;
+#pragma unroll
                     for (int b = a; b < 8; ++b) acc[q++] += J0[a] * J0[b] + J1[a] * J1[b];
                 }
             }
@@ -489,44 +500,55 @@ __device__ bool homography_check_subset(const float* s, const float* d) {
     return negative == 0 || negative == 4;
 }
 
-// Normalised DLT for n >= 4 correspondences given the 9x9 normal matrix LtL (smallest eigenvector by cyclic Jacobi)
-__device__ void jacobi_smallest_eigvec9(double* Amat /* 81, destroyed */, double* Vmat /* 81 */, double* out9) {
+// Normalised DLT for n >= 4 correspondences given the 9x9 normal matrix LtL: smallest eigenvector by cyclic Jacobi.
+// Warp-cooperative: the rotation order, angles and per-element arithmetic are those of the serial sweep; lane r
+// owns row / column r of each rotation's three independent update loops (the serial version on one thread was
+// 163 us of the 390 us homography kernel).  Call with all 32 lanes of one warp; matrices in shared memory.
+__device__ void jacobi_smallest_eigvec9_warp(double* Amat /* 81, destroyed */, double* Vmat /* 81 */,
+                                             double* out9 /* shared */) {
     const int n = 9;
-    for (int i = 0; i < n; ++i)
-        for (int j = 0; j < n; ++j) Vmat[i * n + j] = (i == j) ? 1.0 : 0.0;
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < n * n; i += 32) Vmat[i] = (i / n == i % n) ? 1.0 : 0.0;
+    __syncwarp();
     for (int sweep = 0; sweep < 30; ++sweep) {
         int rotated = 0;
         for (int p = 0; p < n; ++p)
             for (int q = p + 1; q < n; ++q) {
                 const double apq = Amat[p * n + q];
+                const double app = Amat[p * n + p], aqq = Amat[q * n + q];
                 // off-diagonal already below double rounding of the diagonal pair: nothing left to annihilate
-                if (fabs(apq) <= 1e-17 * (fabs(Amat[p * n + p]) + fabs(Amat[q * n + q]))) continue;
+                if (fabs(apq) <= 1e-17 * (fabs(app) + fabs(aqq))) continue;     // warp-uniform
                 ++rotated;
-                const double theta = (Amat[q * n + q] - Amat[p * n + p]) / (2.0 * apq);
+                const double theta = (aqq - app) / (2.0 * apq);
                 const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
                 const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-                for (int r = 0; r < n; ++r) {
+                __syncwarp();                       // everyone has read app / aqq / apq
+                const int r = lane;
+                if (r < n) {
                     const double arp = Amat[r * n + p], arq = Amat[r * n + q];
                     Amat[r * n + p] = c * arp - s * arq;
                     Amat[r * n + q] = s * arp + c * arq;
-                }
-                for (int r = 0; r < n; ++r) {
-                    const double apr = Amat[p * n + r], aqr = Amat[q * n + r];
-                    Amat[p * n + r] = c * apr - s * aqr;
-                    Amat[q * n + r] = s * apr + c * aqr;
-                }
-                for (int r = 0; r < n; ++r) {
                     const double vrp = Vmat[r * n + p], vrq = Vmat[r * n + q];
                     Vmat[r * n + p] = c * vrp - s * vrq;
                     Vmat[r * n + q] = s * vrp + c * vrq;
                 }
+                __syncwarp();
+                if (r < n) {
+                    const double apr = Amat[p * n + r], aqr = Amat[q * n + r];
+                    Amat[p * n + r] = c * apr - s * aqr;
+                    Amat[q * n + r] = s * apr + c * aqr;
+                }
+                __syncwarp();
             }
         if (!rotated) break;
     }
-    int best = 0;
-    for (int i = 1; i < n; ++i)
-        if (Amat[i * n + i] < Amat[best * n + best]) best = i;
-    for (int r = 0; r < n; ++r) out9[r] = Vmat[r * n + best];
+    if (lane == 0) {
+        int best = 0;
+        for (int i = 1; i < n; ++i)
+            if (Amat[i * n + i] < Amat[best * n + best]) best = i;
+        for (int r = 0; r < n; ++r) out9[r] = Vmat[r * n + best];
+    }
+    __syncwarp();
 }
 
 __device__ void denormalise_h(const double* H0, const double* cm, const double* sm, const double* cM, const double* sM,
@@ -583,6 +605,17 @@ __device__ __forceinline__ bool homography_inlier(const float* Hf, const float* 
 }
 
 #define HOM_BATCH 8
+// optional phase timestamps of the homography kernel (scripts/profile_flow.py; not part of the public ABI)
+__device__ unsigned long long* g_hom_dbg = nullptr;
+#define HOM_STAMP(k)                                                               \
+    do {                                                                           \
+        if (g_hom_dbg && threadIdx.x == 0) {                                       \
+            unsigned long long t_;                                                 \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                  \
+            g_hom_dbg[(k)] = t_;                                                   \
+        }                                                                          \
+    } while (0)
+#define HOM_CACHE 1536   // inlier pairs kept in shared memory for the LM passes (24 KB)
 __global__ void __launch_bounds__(256) homography_kernel(const float* __restrict__ all_prev,
                                                           const float* __restrict__ all_cur,
                                                           const unsigned char* __restrict__ status,
@@ -598,9 +631,10 @@ __global__ void __launch_bounds__(256) homography_kernel(const float* __restrict
     __shared__ float s_Hf[HOM_BATCH][8];
     __shared__ int s_done, s_niters, s_maxgood, s_iter, s_fail, s_ninl;
     __shared__ double s_red[8 * 45], s_acc[45], s_work[3 * 64 + 6 * 8 + 8];
-    __shared__ double s_LtL[81], s_V[81], s_nrm[8];
+    __shared__ double s_LtL[81], s_V[81], s_nrm[8], s_h9[9];
     __shared__ CvRng s_rng;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    HOM_STAMP(0);
     const int bg_begin = meta[0];
     const int bg_end = meta[1] - 1;  // `_get_good_match(..., bg_begin, -1)` drops the last point (flow.py:216-217)
     if (tid == 0) { s_n = 0; s_fail = 0; }
@@ -655,6 +689,7 @@ __global__ void __launch_bounds__(256) homography_kernel(const float* __restrict
         if (s_fail) fail_out();
         return;
     }
+    HOM_STAMP(1);
     if (tid == 0) { s_rng.state = 0xffffffffffffffffULL; s_niters = max_iters; s_maxgood = 0; s_iter = 0; s_done = 0; }
     __syncthreads();
     while (true) {
@@ -735,6 +770,8 @@ __global__ void __launch_bounds__(256) homography_kernel(const float* __restrict
         __syncthreads();
         if (s_done) break;
     }
+    HOM_STAMP(2);
+    if (g_hom_dbg && tid == 0) { g_hom_dbg[8] = (unsigned long long)s_iter; g_hom_dbg[9] = (unsigned long long)n; }
     if (s_fail || s_maxgood == 0) { fail_out(); return; }
     // ---- inliers of the best model (ordered) ----
     __shared__ float s_bestf[8];
@@ -761,6 +798,7 @@ __global__ void __launch_bounds__(256) homography_kernel(const float* __restrict
         __syncthreads();
     }
     const int n_in = s_ninl;
+    HOM_STAMP(3);
     // ---- runKernel on all inliers: normalised DLT (HomographyEstimatorCallback::runKernel) ----
     double acc[45];
     {
@@ -795,7 +833,9 @@ __global__ void __launch_bounds__(256) homography_kernel(const float* __restrict
             const double Lx[9] = {X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x};
             const double Ly[9] = {0, 0, 0, X, Y, 1, -y * X, -y * Y, -y};
             int q = 0;
+#pragma unroll
             for (int a = 0; a < 9; ++a)
+#pragma unroll
                 for (int b = a; b < 9; ++b) acc[q++] += Lx[a] * Lx[b] + Ly[a] * Ly[b];
         }
         block_reduce<45>(acc, s_red, s_acc);
@@ -803,21 +843,38 @@ __global__ void __launch_bounds__(256) homography_kernel(const float* __restrict
             int q = 0;
             for (int a = 0; a < 9; ++a)
                 for (int b = a; b < 9; ++b) { s_LtL[a * 9 + b] = s_acc[q]; s_LtL[b * 9 + a] = s_acc[q]; ++q; }
-            double h9[9], H[9];
-            jacobi_smallest_eigvec9(s_LtL, s_V, h9);
-            denormalise_h(h9, cm, sm, cM, sM, H);
+        }
+        __syncthreads();
+        HOM_STAMP(4);
+        if (wid == 0) jacobi_smallest_eigvec9_warp(s_LtL, s_V, s_h9);
+        __syncthreads();
+        if (tid == 0) {
+            double H[9];
+            denormalise_h(s_h9, cm, sm, cM, sM, H);
             for (int i = 0; i < 8; ++i) s_x[i] = H[i];
         }
     } else if (tid == 0) {
         for (int i = 0; i < 8; ++i) s_x[i] = s_best[i];   // runKernel returned 0: H keeps the RANSAC model
     }
     __syncthreads();
+    HOM_STAMP(5);
     // ---- LM refinement (HomographyRefineCallback, 10 iterations) ----
     {
-        HomographyProblem prob{all_prev, all_cur, inl_idx, n_in};
+        __shared__ float4 s_pairs[HOM_CACHE];
+        const bool cached = n_in <= HOM_CACHE;
+        if (cached) {
+            for (int i = tid; i < n_in; i += blockDim.x) {
+                const int p = inl_idx[i];
+                s_pairs[i] = make_float4(all_prev[2 * p], all_prev[2 * p + 1], all_cur[2 * p], all_cur[2 * p + 1]);
+            }
+        }
+        __syncthreads();
+        HomographyProblem prob{all_prev, all_cur, inl_idx, n_in, cached ? s_pairs : nullptr};
         lm_refine(prob, s_x, 10, s_red, s_acc, s_work);
     }
     __syncthreads();
+    HOM_STAMP(6);
+    if (g_hom_dbg && tid == 0) g_hom_dbg[10] = (unsigned long long)n_in;
     if (tid == 0) {
         for (int i = 0; i < 8; ++i) H_out[i] = s_x[i];
         H_out[8] = 1.0;
@@ -833,6 +890,12 @@ __global__ void __launch_bounds__(256) homography_kernel(const float* __restrict
 }
 
 }  // namespace
+
+extern "C" int fm_klt_set_debug(void* dbg) {
+    unsigned long long* p = (unsigned long long*)dbg;
+    cudaMemcpyToSymbol(g_hom_dbg, &p, sizeof(p));
+    return FM_OK;
+}
 
 extern "C" int fm_ransac_homography(const float* all_prev, const float* all_cur, const unsigned char* status,
                                     const int* meta, int max_iters, double confidence, double thresh,

@@ -1,6 +1,7 @@
 // 16-byte vectorised versions of the bandwidth-bound NHWC fp16 layers (8 channels per thread).  Each `fm_vec_*`
 // returns 1 if it handled the call (all channel counts / strides / offsets multiples of 8), 0 otherwise — the
 // scalar kernels in nn.cu remain the general path.
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/fastmot_b200.h"
 
@@ -143,6 +144,88 @@ __global__ void __launch_bounds__(256) dwconv3_vec4(const __half* __restrict__ i
 #pragma unroll
             for (int q = 0; q < 8; ++q) acc[p][q] = act_f(acc[p][q], act);
             st8(out + ((((size_t)b * h + y) * wd) + x0 + p) * c + g * 8, to_h(acc[p]));
+        }
+    }
+}
+
+// depthwise 3x3, shared-memory tiled: one CTA owns DW_R output rows of one image (all columns, all channels), stages
+// the DW_R + 2 input rows once with cp.async (zero-filled above / below the image) and computes from shared memory.
+// The untiled kernel above re-fetches every input pixel ~4.5x through L1/L2 (3 rows x 1.5 column overlap), which is
+// what bounded it at ~2 TB/s of useful traffic; here HBM sees (DW_R + 2) / DW_R reads + 1 write.
+constexpr int DW_R = 8;
+
+__global__ void __launch_bounds__(256) dwconv3_tile(const __half* __restrict__ in, const __half* __restrict__ w,
+                                                     const float* __restrict__ bias, __half* __restrict__ out, int h,
+                                                     int wd, int c, int act) {
+    extern __shared__ __align__(16) unsigned char dw_smem[];
+    __half* tile = reinterpret_cast<__half*>(dw_smem);                       // [(DW_R+2)][wd][c]
+    __half* sw = tile + (size_t)(DW_R + 2) * wd * c;                         // [9][c]
+    const int cg = c >> 3, xg = wd >> 2;
+    const int b = blockIdx.y, y0 = blockIdx.x * DW_R;
+    const int rows_in = DW_R + 2;
+    const __half* img = in + (size_t)b * h * wd * c;
+    // ---- stage rows y0-1 .. y0+DW_R (16-byte chunks; rows outside the image are zero-filled) ----
+    const int row_chunks = wd * cg;
+    for (int i = threadIdx.x; i < rows_in * row_chunks; i += blockDim.x) {
+        const int r = i / row_chunks, k = i - r * row_chunks;
+        const int yy = y0 - 1 + r;
+        const bool ok = yy >= 0 && yy < h;
+        const __half* src = ok ? img + ((size_t)yy * row_chunks + k) * 8 : img;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + (size_t)i * 8);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u));
+    }
+    for (int i = threadIdx.x; i < 9 * cg; i += blockDim.x) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(sw + (size_t)i * 8);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, 16;" ::"r"(dst), "l"(w + (size_t)i * 8));
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // ---- compute: item = (row, 4-pixel group, 8-channel group) ----
+    const int items = DW_R * xg * cg;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+        const int g = it % cg;
+        int t = it / cg;
+        const int x0 = (t % xg) * 4;
+        const int ry = t / xg;
+        const int y = y0 + ry;
+        if (y >= h) break;                       // items are row-major: everything after is out of range too
+        float acc[4][8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float bq = bias ? bias[g * 8 + q] : 0.f;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[p][q] = bq;
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const __half* row = tile + ((size_t)(ry + r) * wd) * c + g * 8;
+            float ww[3][8];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) to_f(ld8(sw + (size_t)(r * 3 + k) * c + g * 8), ww[k]);
+#pragma unroll
+            for (int cx = 0; cx < 6; ++cx) {
+                const int xx = x0 + cx - 1;
+                H8 v;
+                if (xx >= 0 && xx < wd) v = ld8(row + (size_t)xx * c);
+                else v.u = make_uint4(0u, 0u, 0u, 0u);
+                float a[8];
+                to_f(v, a);
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const int s = cx - p;          // tap column for output pixel p
+                    if (s < 0 || s > 2) continue;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) acc[p][q] += a[q] * ww[s][q];
+                }
+            }
+        }
+        __half* orow = out + (((size_t)b * h + y) * wd + x0) * c + g * 8;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[p][q] = act_f(acc[p][q], act);
+            st8(orow + (size_t)p * c, to_h(acc[p]));
         }
     }
 }
@@ -307,6 +390,20 @@ int fm_vec_dwconv3(const void* in, const void* w, const float* bias, void* out, 
                    cudaStream_t s) {
     if (!al8(c)) return 0;
     if ((wd & 3) == 0) {
+        const size_t tile_bytes = ((size_t)(DW_R + 2) * wd + 9) * c * sizeof(__half);
+        static int use_tile = -1;          // FM_DW_TILE=0 falls back to the untiled kernel (A/B timing only)
+        if (use_tile < 0) { const char* e = getenv("FM_DW_TILE"); use_tile = (e && e[0] == '0') ? 0 : 1; }
+        if (use_tile && tile_bytes <= 96 * 1024 && h >= DW_R) {
+            static size_t attr_bytes = 0;
+            if (tile_bytes > attr_bytes) {
+                cudaFuncSetAttribute(dwconv3_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 * 1024));
+                attr_bytes = 96 * 1024;
+            }
+            dim3 grid((h + DW_R - 1) / DW_R, n);
+            dwconv3_tile<<<grid, 256, tile_bytes, s>>>((const __half*)in, (const __half*)w, bias, (__half*)out, h, wd, c,
+                                                       act);
+            return 1;
+        }
         const size_t total4 = (size_t)n * h * (wd >> 2) * (c >> 3);
         dwconv3_vec4<<<vgrid(total4), 256, 0, s>>>((const __half*)in, (const __half*)w, bias, (__half*)out, n, h, wd, c,
                                                    act);

@@ -242,7 +242,9 @@ class Flow:
         self._bg_cache = None
         rounds = 0
         while True:
-            step = 2
+            # rounds past the fixed point exit at once on the device, so four per host round trip cost two ~3 us
+            # launches when two would have done and save a sync + status read when they would not
+            step = 4
             _lib.check(lib.fm_ransac_affine_partial_batch(
                 ptr(self.all_prev), ptr(self.all_cur), ptr(self.status), ptr(self.trk_begin), ptr(self.slots_dev), n,
                 step, C.c_void_p(fl + 32), None, ptr(self.est_boxes), ptr(self.sig), ptr(pool.tlbr),

@@ -52,3 +52,22 @@ for (n, h, w, cin, cout, k, st) in SHAPES:
               "first tmem_ld32 ns:", int((t[:, 7] - t[:, 4]).mean()))
         dbg.zero_()
     print(f"{(n,h,w,cin,cout,k,st)}: {us:8.1f} us  {flops/us/1e6:8.1f} TFLOP/s  {byts/us/1e3:7.1f} GB/s(min traffic)")
+
+# ---- depthwise 3x3 (OSNet Lite 3x3) ----
+if not ONLY:
+    for (n, h, w, c) in [(224, 64, 32, 64), (224, 32, 16, 96), (224, 16, 8, 128)]:
+        x = torch.randn(n, h, w, c, device="cuda").half()
+        wt = torch.randn(9, c, device="cuda").half()
+        b = torch.zeros(c, device="cuda")
+        y = torch.empty_like(x)
+        ts = []
+        for it in range(6):
+            flush.fill_(it)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            lib.fm_dwconv3(ptr(x), ptr(wt), ptr(b), ptr(y), n, h, w, c, 5, stream_ptr())
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        us = sorted(ts[1:])[len(ts[1:]) // 2]
+        print(f"dw3x3 {(n,h,w,c)}: {us:8.1f} us   {2 * x.numel() * 2 / us / 1e3:7.1f} GB/s(min traffic)")

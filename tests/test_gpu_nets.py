@@ -117,6 +117,32 @@ def _yolo_vs_oracle(name, hw, tol):
     return eng
 
 
+@pytest.mark.parametrize("shape", [
+    (3, 64, 32, 64),     # OSNet stage 1 geometry: shared-memory tiled kernel, 8 full strips
+    (2, 20, 12, 24),     # ragged last strip (20 = 2 * 8 + 4), 3 channel groups
+    (2, 16, 8, 128),     # stage 3 geometry
+    (1, 5, 8, 16),       # fewer rows than a strip: untiled vec4 kernel
+    (1, 9, 7, 8),        # width not a multiple of 4: per-pixel kernel
+])
+def test_dwconv3_vs_torch(shape):
+    """Depthwise 3x3 s1 p1 + bias + ReLU (OSNet Lite 3x3 second half) on every kernel variant."""
+    from fastmot_b200 import _lib
+    from fastmot_b200.devmem import ptr, stream_ptr
+    lib = _lib.require_device()
+    n, h, w, c = shape
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(n, h, w, c, generator=g).half()
+    wt = (torch.randn(9, c, generator=g) * 0.3).half()
+    b = torch.randn(c, generator=g) * 0.1
+    xd, wd_, bd = x.cuda(), wt.cuda(), b.cuda()
+    out = torch.empty(n, h, w, c, dtype=torch.float16, device="cuda")
+    _lib.check(lib.fm_dwconv3(ptr(xd), ptr(wd_), ptr(bd), ptr(out), n, h, w, c, 5, stream_ptr()), "fm_dwconv3")
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float().t().reshape(c, 1, 3, 3), b, padding=1, groups=c)
+    ref = F.relu(ref).permute(0, 2, 3, 1)
+    assert _rel(out.float().cpu(), ref) < 5e-3
+
+
 def test_yolov4_tiny_engine_vs_oracle():
     eng = _yolo_vs_oracle('yolov4-tiny', (416, 416), 2e-2)
     assert eng.n_tc + eng.n_simt == 21
