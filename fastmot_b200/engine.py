@@ -64,12 +64,15 @@ class _Net:
         self._graph = None
         self._keep = []
         self.n_tc = self.n_simt = 0
+        self.layer_bytes = 0        # algorithmic HBM bytes of the conv / depthwise layers (each tensor moved once)
         self.dev = torch.device("cuda")
         _ensure_workspace(self._lib, self.dev)
 
     def _conv(self, desc, x, w, b, out, residual=None):
         lib = self._lib
         self._keep.append(desc)
+        self.layer_bytes += 2 * (desc.n * desc.hi * desc.wi * desc.cin + desc.n * desc.ho * desc.wo * desc.cout
+                                 * (2 if residual is not None else 1) + desc.kh * desc.kw * desc.cin * desc.cout)
         if self.use_tc and lib.fm_conv2d_tc_supported(C.byref(desc)):
             fn = lib.fm_conv2d_tc
             self.n_tc += 1
@@ -307,6 +310,7 @@ class OSNetEngine(_Net):
                 params[name] = (wd, bd)
                 y = alloc(B * h * w * c)
                 self._add('fm_dwconv3', ptr(x), ptr(wd), ptr(bd), ptr(y), B, h, w, c, _ACT[act])
+                self.layer_bytes += 2 * (2 * B * h * w * c + 9 * c)
                 new = (dst, (y, c, h, w))
             elif kind == 'maxpool3s2':
                 x, xc, h, w = live[op[1]]
@@ -409,16 +413,19 @@ class _Profiler:
     def reset(self):
         self.records = []
 
-    def add(self, kind, e0, e1, flops, path):
-        self.records.append((kind, e0, e1, flops, path))
+    def add(self, kind, e0, e1, flops, path, nbytes=0.0):
+        self.records.append((kind, e0, e1, flops, path, nbytes))
 
     def summary(self):
         torch.cuda.synchronize()
-        out = {"yolo_ms": 0.0, "osnet_ms": 0.0, "yolo_flops": 0.0, "osnet_flops": 0.0, "detector_frames": 0}
+        out = {"yolo_ms": 0.0, "osnet_ms": 0.0, "yolo_flops": 0.0, "osnet_flops": 0.0, "yolo_bytes": 0.0,
+               "osnet_bytes": 0.0, "yolo_calls": 0, "osnet_calls": 0, "detector_frames": 0}
         path = set()
-        for kind, e0, e1, flops, p in self.records:
+        for kind, e0, e1, flops, p, nbytes in self.records:
             out[kind + "_ms"] += e0.elapsed_time(e1)
             out[kind + "_flops"] += flops
+            out[kind + "_bytes"] += nbytes
+            out[kind + "_calls"] += 1
             out["detector_frames"] += kind == "yolo"
             path.add(p)
         out["conv_path"] = "+".join(sorted(path)) if path else None
@@ -449,7 +456,7 @@ def _profiled(kind):
                 n = a[0] if a and a[0] is not None else self.max_batch
                 flops = 2.0 * self.macs_per_crop * n
             path = "tcgen05" if self.n_tc >= self.n_simt else "simt"
-            _PROF.add(kind, e0, e1, flops, f"{kind}:{path}({self.n_tc}tc/{self.n_simt}simt)")
+            _PROF.add(kind, e0, e1, flops, f"{kind}:{path}({self.n_tc}tc/{self.n_simt}simt)", float(self.layer_bytes))
             return r
         return wrapper
     return deco
