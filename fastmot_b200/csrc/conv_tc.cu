@@ -870,8 +870,13 @@ extern "C" int fm_conv2d_tc(const FmConvDesc* d, const void* in, const void* wgt
         else if (nk <= 2) launch_tc<32, 2>(d, in, wgt, bias, residual, out, s);
         else launch_tc<32, 4>(d, in, wgt, bias, residual, out, s);
     } else if (bn == 64) {
+        static int st64 = -1;          // FM_CONV_ST64=2|3 overrides the ring depth of the 64-wide deep-K kernel (experiments)
+        if (st64 < 0) { const char* e = getenv("FM_CONV_ST64"); st64 = e ? atoi(e) : 0; }
         if (nk == 1) launch_tc<64, 1>(d, in, wgt, bias, residual, out, s);
-        else if (nk <= 2) launch_tc<64, 2>(d, in, wgt, bias, residual, out, s);
+        // many waves of tiles (the OSNet 7x7 stem: 14 k tiles): residency beats ring depth (727 -> 457 us measured)
+        else if (nk <= 2 || st64 == 2 || (st64 == 0 && m_tiles_all >= 8 * FM_NUM_SMS))
+            launch_tc<64, 2>(d, in, wgt, bias, residual, out, s);
+        else if (st64 == 3) launch_tc<64, 3>(d, in, wgt, bias, residual, out, s);
         else launch_tc<64, 4>(d, in, wgt, bias, residual, out, s);
     } else {
         if (nk == 1) launch_tc<128, 1>(d, in, wgt, bias, residual, out, s);

@@ -83,12 +83,66 @@ __device__ bool solve_dense(double* A, double* b, int n) {
     return true;
 }
 
+// The same elimination run by one warp: lane k owns column k of the system (lane N the right-hand side), the pivot
+// search and the row factors are computed redundantly from broadcast shared-memory reads, so every element sees the
+// operations of solve_dense in the same order (bit-identical result) while a column step costs one dependent
+// shared-memory round instead of ~N^2.  Call with all 32 lanes; A / b in shared memory.
+template <int N>
+__device__ __forceinline__ bool solve_dense_warp(double* A, double* b) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+        int piv = c;
+        double best = fabs(A[c * N + c]);
+#pragma unroll
+        for (int r = c + 1; r < N; ++r) {
+            const double v = fabs(A[r * N + c]);
+            if (v > best) { best = v; piv = r; }
+        }
+        if (!(best > 0.0)) return false;                 // warp-uniform
+        __syncwarp();
+        if (piv != c) {
+            if (lane < N) { const double t = A[c * N + lane]; A[c * N + lane] = A[piv * N + lane]; A[piv * N + lane] = t; }
+            else if (lane == N) { const double t = b[c]; b[c] = b[piv]; b[piv] = t; }
+        }
+        __syncwarp();
+        const double inv = 1.0 / A[c * N + c];
+        double f[N];
+#pragma unroll
+        for (int r = c + 1; r < N; ++r) f[r] = A[r * N + c] * inv;
+        __syncwarp();                                    // every lane holds the factors before column c changes
+        if (lane >= c && lane < N) {
+            const double acl = A[c * N + lane];
+#pragma unroll
+            for (int r = c + 1; r < N; ++r)
+                if (f[r] != 0.0) A[r * N + lane] -= f[r] * acl;
+        } else if (lane == N) {
+            const double bc = b[c];
+#pragma unroll
+            for (int r = c + 1; r < N; ++r)
+                if (f[r] != 0.0) b[r] -= f[r] * bc;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        for (int r = N - 1; r >= 0; --r) {
+            double v = b[r];
+            for (int k = r + 1; k < N; ++k) v -= A[r * N + k] * b[k];
+            b[r] = v / A[r * N + r];
+        }
+    }
+    __syncwarp();
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------ LM (levmarq.cpp)
 // Problem concept: static const int NP; void accumulate(const double* x, bool need_jac, double* acc) where
 // acc = [S, v[NP], A upper-triangular row-major NP(NP+1)/2]; block-parallel, result reduced into s_acc.
+// The scalar bookkeeping between the block-wide passes (normal-equation solve, gain ratio, lambda schedule) is run
+// by warp 0 cooperatively; it used to be one thread walking shared memory and was most of each iteration.
 template <class Problem>
-__device__ __forceinline__ void lm_refine(Problem& prob, double* x /* shared [NP] */, int max_iters, double* s_red, double* s_acc,
-                          double* s_work /* >= 3*NP*NP + 6*NP doubles */) {
+__device__ __forceinline__ void lm_refine(Problem& prob, double* x /* shared [NP] */, int max_iters, double* s_red,
+                                          double* s_acc, double* s_work /* >= 3*NP*NP + 6*NP doubles */) {
     constexpr int NP = Problem::NP;
     constexpr int NA = 1 + NP + NP * (NP + 1) / 2;
     double* A = s_work;                 // NP*NP
@@ -100,63 +154,92 @@ __device__ __forceinline__ void lm_refine(Problem& prob, double* x /* shared [NP
     double* tmp = Dg + NP;              // NP*NP + NP scratch
     __shared__ double s_S, s_lambda, s_lc;
     __shared__ int s_proceed;
+    const int lane = threadIdx.x & 31;
+    const bool w0 = threadIdx.x < 32;
+    // unpack the reduced [S, v, upper(A)] into the symmetric matrix (warp 0; index map computed per element)
+    auto unpack = [&]() {
+        if (lane == 0) s_S = s_acc[0];
+        if (lane < NP) v[lane] = s_acc[1 + lane];
+        for (int e = lane; e < NP * NP; e += 32) {
+            const int i = e / NP, j = e - i * NP;
+            const int lo = i < j ? i : j, hi = i < j ? j : i;
+            A[e] = s_acc[1 + NP + lo * NP - lo * (lo - 1) / 2 + (hi - lo)];
+        }
+    };
     double acc[NA];
     prob.accumulate(x, true, acc);
     block_reduce<NA>(acc, s_red, s_acc);
-    if (threadIdx.x == 0) {
-        s_S = s_acc[0];
-        int q = 1 + NP;
-        for (int i = 0; i < NP; ++i) v[i] = s_acc[1 + i];
-        for (int i = 0; i < NP; ++i)
-            for (int j = i; j < NP; ++j) { A[i * NP + j] = s_acc[q]; A[j * NP + i] = s_acc[q]; ++q; }
-        for (int i = 0; i < NP; ++i) Dg[i] = A[i * NP + i];
-        s_lambda = 1.0; s_lc = 0.75; s_proceed = 1;
+    if (w0) {
+        unpack();
+        __syncwarp();
+        if (lane < NP) Dg[lane] = A[lane * NP + lane];
+        if (lane == 0) { s_lambda = 1.0; s_lc = 0.75; s_proceed = 1; }
     }
     __syncthreads();
     for (int iter = 0; iter < max_iters; ++iter) {
-        if (threadIdx.x == 0) {
-            for (int i = 0; i < NP * NP; ++i) Ap[i] = A[i];
-            for (int i = 0; i < NP; ++i) { Ap[i * NP + i] += Dg[i] * s_lambda; d[i] = v[i]; }
-            if (!solve_dense(Ap, d, NP))
-                for (int i = 0; i < NP; ++i) d[i] = 0.0;
-            for (int i = 0; i < NP; ++i) xd[i] = x[i] - d[i];
+        if (w0) {
+            const double lambda = s_lambda;
+            for (int e = lane; e < NP * NP; e += 32) {
+                const int i = e / NP, j = e - i * NP;
+                Ap[e] = A[e] + (i == j ? Dg[i] * lambda : 0.0);
+            }
+            if (lane < NP) d[lane] = v[lane];
+            __syncwarp();
+            const bool ok = solve_dense_warp<NP>(Ap, d);
+            if (lane < NP) {
+                if (!ok) d[lane] = 0.0;
+                xd[lane] = x[lane] - d[lane];
+            }
         }
         __syncthreads();
         prob.accumulate(xd, false, acc);
         block_reduce<1>(acc, s_red, s_acc);      // only the residual norm is needed for the trial step
         const bool improved = s_acc[0] < s_S;
-        if (threadIdx.x == 0) {
+        if (w0) {
             const double Sd = s_acc[0], S = s_S;
-            double dS = 0.0, dv = 0.0, dinf = 0.0;
-            for (int i = 0; i < NP; ++i) {
+            // dS = sum_i d_i (2 v_i - (A d)_i), dv = d.v, dinf = max |d_i|: lane i forms its term, lane 0 adds them
+            // in index order (the order of the scalar loop)
+            double term_s = 0.0, term_v = 0.0, term_i = 0.0;
+            if (lane < NP) {
                 double Ad = 0.0;
-                for (int j = 0; j < NP; ++j) Ad += A[i * NP + j] * d[j];
-                dS += d[i] * (2.0 * v[i] - Ad);
-                dv += d[i] * v[i];
-                dinf = fmax(dinf, fabs(d[i]));
+                for (int j = 0; j < NP; ++j) Ad += A[lane * NP + j] * d[j];
+                term_s = d[lane] * (2.0 * v[lane] - Ad);
+                term_v = d[lane] * v[lane];
+                term_i = fabs(d[lane]);
+            }
+            double dS = 0.0, dv = 0.0, dinf = 0.0;
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                dS += __shfl_sync(0xffffffffu, term_s, i);
+                dv += __shfl_sync(0xffffffffu, term_v, i);
+                dinf = fmax(dinf, __shfl_sync(0xffffffffu, term_i, i));
             }
             const double R = (S - Sd) / (fabs(dS) > DBL_EPSILON ? dS : 1.0);
+            double lambda = s_lambda, lc = s_lc;       // every lane tracks the schedule; lane 0 publishes it
             if (R > 0.75) {
-                s_lambda *= 0.5;
-                if (s_lambda < s_lc) s_lambda = 0.0;
+                lambda *= 0.5;
+                if (lambda < lc) lambda = 0.0;
             } else if (R < 0.25) {
                 double nu = (Sd - S) / (fabs(dv) > DBL_EPSILON ? dv : 1.0) + 2.0;
                 nu = fmin(fmax(nu, 2.0), 10.0);
-                if (s_lambda == 0.0) {
+                if (lambda == 0.0) {
                     // lambda = lc = 1 / max |diag(A^-1)|
                     double maxval = DBL_EPSILON;
                     for (int c = 0; c < NP; ++c) {
-                        for (int i = 0; i < NP * NP; ++i) tmp[i] = A[i];
-                        double* e = tmp + NP * NP;
-                        for (int i = 0; i < NP; ++i) e[i] = (i == c) ? 1.0 : 0.0;
-                        if (solve_dense(tmp, e, NP)) maxval = fmax(maxval, fabs(e[c]));
+                        __syncwarp();
+                        for (int e = lane; e < NP * NP; e += 32) tmp[e] = A[e];
+                        double* ev = tmp + NP * NP;
+                        if (lane < NP) ev[lane] = (lane == c) ? 1.0 : 0.0;
+                        __syncwarp();
+                        if (solve_dense_warp<NP>(tmp, ev)) maxval = fmax(maxval, fabs(ev[c]));
                     }
-                    s_lambda = s_lc = 1.0 / maxval;
+                    lambda = lc = 1.0 / maxval;
                     nu *= 0.5;
                 }
-                s_lambda *= nu;
+                lambda *= nu;
             }
-            tmp[0] = dinf;
+            __syncwarp();
+            if (lane == 0) { s_lambda = lambda; s_lc = lc; tmp[0] = dinf; }
         }
         __syncthreads();
         if (improved) {
@@ -164,13 +247,7 @@ __device__ __forceinline__ void lm_refine(Problem& prob, double* x /* shared [NP
             __syncthreads();
             prob.accumulate(x, true, acc);
             block_reduce<NA>(acc, s_red, s_acc);
-            if (threadIdx.x == 0) {
-                s_S = s_acc[0];
-                int q = 1 + NP;
-                for (int i = 0; i < NP; ++i) v[i] = s_acc[1 + i];
-                for (int i = 0; i < NP; ++i)
-                    for (int j = i; j < NP; ++j) { A[i * NP + j] = s_acc[q]; A[j * NP + i] = s_acc[q]; ++q; }
-            }
+            if (w0) unpack();
         }
         if (threadIdx.x == 0) {
             // proceed = iter+1 < maxIters && |d|_inf >= eps && |r|_inf >= eps (r_inf approximated by sqrt(S)).
@@ -500,46 +577,68 @@ __device__ bool homography_check_subset(const float* s, const float* d) {
     return negative == 0 || negative == 4;
 }
 
-// Normalised DLT for n >= 4 correspondences given the 9x9 normal matrix LtL: smallest eigenvector by cyclic Jacobi.
-// Warp-cooperative: the rotation order, angles and per-element arithmetic are those of the serial sweep; lane r
-// owns row / column r of each rotation's three independent update loops (the serial version on one thread was
-// 163 us of the 390 us homography kernel).  Call with all 32 lanes of one warp; matrices in shared memory.
+// Normalised DLT for n >= 4 correspondences given the 9x9 normal matrix LtL: smallest eigenvector by Jacobi rotations.
+// One warp, round-robin ("chess tournament") ordering: each of the 9 rounds of a sweep applies 4 rotations on disjoint
+// index pairs at once -- lanes 0..3 derive the angles, then 36 (rotation, row) tasks update the columns of A and V and
+// 36 more the rows of A.  A sweep is 9 dependent steps instead of 36; every rotation is the textbook one
+// (t = sgn(theta) / (|theta| + sqrt(theta^2 + 1))), only their order differs from a cyclic-by-row sweep, which changes
+// the result at rounding level (H is refined by LM afterwards).  The serial sweep on one thread took 163 us.
 __device__ void jacobi_smallest_eigvec9_warp(double* Amat /* 81, destroyed */, double* Vmat /* 81 */,
                                              double* out9 /* shared */) {
-    const int n = 9;
+    constexpr int n = 9;
+    __shared__ double s_cs[4][2];
+    __shared__ int s_pq[4][2];
     const int lane = threadIdx.x & 31;
     for (int i = lane; i < n * n; i += 32) Vmat[i] = (i / n == i % n) ? 1.0 : 0.0;
     __syncwarp();
     for (int sweep = 0; sweep < 30; ++sweep) {
-        int rotated = 0;
-        for (int p = 0; p < n; ++p)
-            for (int q = p + 1; q < n; ++q) {
-                const double apq = Amat[p * n + q];
-                const double app = Amat[p * n + p], aqq = Amat[q * n + q];
+        bool rotated = false;
+        for (int round = 0; round < n; ++round) {
+            bool act = false;
+            if (lane < 4) {
+                int p = (round + lane + 1) % n, q = (round - (lane + 1) + n) % n;
+                if (p > q) { const int t = p; p = q; q = t; }
+                const double apq = Amat[p * n + q], app = Amat[p * n + p], aqq = Amat[q * n + q];
+                double c = 1.0, sn = 0.0;
                 // off-diagonal already below double rounding of the diagonal pair: nothing left to annihilate
-                if (fabs(apq) <= 1e-17 * (fabs(app) + fabs(aqq))) continue;     // warp-uniform
-                ++rotated;
-                const double theta = (aqq - app) / (2.0 * apq);
-                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-                __syncwarp();                       // everyone has read app / aqq / apq
-                const int r = lane;
-                if (r < n) {
-                    const double arp = Amat[r * n + p], arq = Amat[r * n + q];
-                    Amat[r * n + p] = c * arp - s * arq;
-                    Amat[r * n + q] = s * arp + c * arq;
-                    const double vrp = Vmat[r * n + p], vrq = Vmat[r * n + q];
-                    Vmat[r * n + p] = c * vrp - s * vrq;
-                    Vmat[r * n + q] = s * vrp + c * vrq;
+                if (fabs(apq) > 1e-17 * (fabs(app) + fabs(aqq))) {
+                    act = true;
+                    const double theta = (aqq - app) / (2.0 * apq);
+                    const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                    c = 1.0 / sqrt(t * t + 1.0);
+                    sn = t * c;
                 }
-                __syncwarp();
-                if (r < n) {
-                    const double apr = Amat[p * n + r], aqr = Amat[q * n + r];
-                    Amat[p * n + r] = c * apr - s * aqr;
-                    Amat[q * n + r] = s * apr + c * aqr;
-                }
-                __syncwarp();
+                s_cs[lane][0] = c; s_cs[lane][1] = sn;
+                s_pq[lane][0] = p; s_pq[lane][1] = act ? q : -1;
             }
+            const unsigned any = __ballot_sync(0xffffffffu, act);
+            if (!any) continue;                               // warp-uniform
+            rotated = true;
+            __syncwarp();
+            for (int idx = lane; idx < 4 * n; idx += 32) {     // columns p, q of A and V, row r
+                const int k = idx / n, r = idx - k * n;
+                const int p = s_pq[k][0], q = s_pq[k][1];
+                if (q < 0) continue;
+                const double c = s_cs[k][0], sn = s_cs[k][1];
+                const double arp = Amat[r * n + p], arq = Amat[r * n + q];
+                Amat[r * n + p] = c * arp - sn * arq;
+                Amat[r * n + q] = sn * arp + c * arq;
+                const double vrp = Vmat[r * n + p], vrq = Vmat[r * n + q];
+                Vmat[r * n + p] = c * vrp - sn * vrq;
+                Vmat[r * n + q] = sn * vrp + c * vrq;
+            }
+            __syncwarp();
+            for (int idx = lane; idx < 4 * n; idx += 32) {     // rows p, q of A, column r
+                const int k = idx / n, r = idx - k * n;
+                const int p = s_pq[k][0], q = s_pq[k][1];
+                if (q < 0) continue;
+                const double c = s_cs[k][0], sn = s_cs[k][1];
+                const double apr = Amat[p * n + r], aqr = Amat[q * n + r];
+                Amat[p * n + r] = c * apr - sn * aqr;
+                Amat[q * n + r] = sn * apr + c * aqr;
+            }
+            __syncwarp();
+        }
         if (!rotated) break;
     }
     if (lane == 0) {

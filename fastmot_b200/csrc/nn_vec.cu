@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256) dwconv3_vec4(const __half* __restrict__ i
 // what bounded it at ~2 TB/s of useful traffic; here HBM sees (DW_R + 2) / DW_R reads + 1 write.
 constexpr int DW_R = 8;
 
-__global__ void __launch_bounds__(256) dwconv3_tile(const __half* __restrict__ in, const __half* __restrict__ w,
+__global__ void __launch_bounds__(256, 3) dwconv3_tile(const __half* __restrict__ in, const __half* __restrict__ w,
                                                      const float* __restrict__ bias, __half* __restrict__ out, int h,
                                                      int wd, int c, int act) {
     extern __shared__ __align__(16) unsigned char dw_smem[];
@@ -164,13 +164,14 @@ __global__ void __launch_bounds__(256) dwconv3_tile(const __half* __restrict__ i
     const int b = blockIdx.y, y0 = blockIdx.x * DW_R;
     const int rows_in = DW_R + 2;
     const __half* img = in + (size_t)b * h * wd * c;
-    // ---- stage rows y0-1 .. y0+DW_R (16-byte chunks; rows outside the image are zero-filled) ----
+    // ---- stage rows y0-1 .. y0+DW_R: they are one contiguous run of 16-byte chunks in the image (full-width rows), so
+    // chunk i of the tile is chunk first + i of the image; chunks before / after the image are zero-filled ----
     const int row_chunks = wd * cg;
+    const int first = (y0 - 1) * row_chunks, img_chunks = h * row_chunks;
     for (int i = threadIdx.x; i < rows_in * row_chunks; i += blockDim.x) {
-        const int r = i / row_chunks, k = i - r * row_chunks;
-        const int yy = y0 - 1 + r;
-        const bool ok = yy >= 0 && yy < h;
-        const __half* src = ok ? img + ((size_t)yy * row_chunks + k) * 8 : img;
+        const int gi = first + i;
+        const bool ok = gi >= 0 && gi < img_chunks;
+        const __half* src = img + (size_t)(ok ? gi : 0) * 8;
         const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + (size_t)i * 8);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u));
     }
