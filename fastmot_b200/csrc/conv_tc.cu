@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    fm_pdl_trigger();
     DBG_STAMP(0);
     const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
     const int M = d.n * d.ho * d.wo;
@@ -419,6 +420,9 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
         }
     };
 
+    // everything above is independent of other kernels' output; the activations (and the split-K workspace /
+    // output buffers, which an earlier kernel may still be reading) are not
+    fm_pdl_wait();
 #pragma unroll
     for (int p = 0; p < STAGES - 1; ++p) {
         if (p < nk) issue_loads(p, p);
@@ -708,6 +712,8 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(FmConvDesc d, const 
                                                              const float* __restrict__ bias,
                                                              const __half* __restrict__ residual,
                                                              __half* __restrict__ out) {
+    fm_pdl_trigger();
+    fm_pdl_wait();
     const int M = d.n * d.ho * d.wo;
     const size_t total = (size_t)M * d.cout;
     const int act = d.act & 0xff;
@@ -794,12 +800,13 @@ int launch_tc(const FmConvDesc* d, const void* in, const void* wgt, const float*
             if ((long long)splits * M * d->cout * 4 <= g_ws_bytes) grid.z = splits; else sps = nk;
         }
     }
-    conv_tc_kernel<BN, STAGES><<<grid, 128, smem, s>>>(*d, (const __half*)in, (const __half*)wgt, bias,
-                                                       (const __half*)residual, (__half*)out, g_ws, sps);
+    fm_launch_pdl(conv_tc_kernel<BN, STAGES>, grid, dim3(128), (size_t)smem, s, *d, (const __half*)in,
+                  (const __half*)wgt, bias, (const __half*)residual, (__half*)out, g_ws, sps);
     if (grid.z > 1) {
         const size_t total = (size_t)M * d->cout;
         const int blocks = (int)((total + 255) / 256 < (size_t)FM_NUM_SMS * 8 ? (total + 255) / 256 : FM_NUM_SMS * 8);
-        splitk_reduce_kernel<<<blocks, 256, 0, s>>>(*d, g_ws, (int)grid.z, bias, (const __half*)residual, (__half*)out);
+        fm_launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), (size_t)0, s, *d, (const float*)g_ws, (int)grid.z,
+                      bias, (const __half*)residual, (__half*)out);
         fm_count_launches(1);
     }
     return 0;
