@@ -792,7 +792,10 @@ int launch_tc(const FmConvDesc* d, const void* in, const void* wgt, const float*
     // split-K when the output tiling alone cannot fill the 148 SMs (batch-1 deep layers)
     const int tiles = grid.x * grid.y;
     if (g_ws && tiles * 2 <= FM_NUM_SMS && nk >= 8) {
-        int want = (FM_NUM_SMS + tiles - 1) / tiles;
+        // as many K splits as still fit in ONE wave of resident CTAs: a 149th CTA on 148 single-CTA SMs runs after the
+        // others and doubles the layer time (seen on the 40x40 and 20x20 YOLO layers: 156 / 160 CTAs, 2 waves)
+        constexpr int per_sm = (227 * 1024) / (smem + 1024) > 0 ? (227 * 1024) / (smem + 1024) : 1;
+        int want = FM_NUM_SMS * per_sm / tiles;
         if (want > nk / 4) want = nk / 4;
         if (want > 1) {
             sps = (nk + want - 1) / want;
@@ -872,23 +875,30 @@ extern "C" int fm_conv2d_tc(const FmConvDesc* d, const void* in, const void* wgt
         if (tiles128 > FM_NUM_SMS / 2 && tiles128 < 2 * FM_NUM_SMS) bn = 64;
     }
     if (force_bn) bn = force_bn;
+    // Ring depth: deep rings hide the gather latency of a long K loop, but they cost residency (6 x 32 KB = one CTA
+    // per SM).  What decides is how the tile count sits against one wave of resident CTAs:
+    //   * the layer fits in one wave at the deep setting          -> deep ring (and split-K fills the idle SMs),
+    //   * it fits in one wave only with a shallower ring          -> that ring (a second, mostly empty wave doubles
+    //                                                                the layer time),
+    //   * many waves either way (OSNet stem, first YOLO layers)   -> shallow ring, residency hides the latency.
+    static int rules = -1;          // FM_CONV_RULES=0 restores the K-only rule (A/B timing)
+    if (rules < 0) { const char* e = getenv("FM_CONV_RULES"); rules = (e && e[0] == '0') ? 0 : 1; }
+    const int tiles = m_tiles_all * ((d->cout + bn - 1) / bn);
     if (bn == 32) {
         if (nk == 1) launch_tc<32, 1>(d, in, wgt, bias, residual, out, s);
-        else if (nk <= 2) launch_tc<32, 2>(d, in, wgt, bias, residual, out, s);
+        else if (nk <= 2 || (rules && tiles > 5 * FM_NUM_SMS)) launch_tc<32, 2>(d, in, wgt, bias, residual, out, s);
         else launch_tc<32, 4>(d, in, wgt, bias, residual, out, s);
     } else if (bn == 64) {
-        static int st64 = -1;          // FM_CONV_ST64=2|3 overrides the ring depth of the 64-wide deep-K kernel (experiments)
-        if (st64 < 0) { const char* e = getenv("FM_CONV_ST64"); st64 = e ? atoi(e) : 0; }
+        // 64-wide: 4 stages = 96 KB (2 CTAs / SM), 2 stages = 48 KB (4 / SM)
         if (nk == 1) launch_tc<64, 1>(d, in, wgt, bias, residual, out, s);
-        // many waves of tiles (the OSNet 7x7 stem: 14 k tiles): residency beats ring depth (727 -> 457 us measured)
-        else if (nk <= 2 || st64 == 2 || (st64 == 0 && m_tiles_all >= 8 * FM_NUM_SMS))
-            launch_tc<64, 2>(d, in, wgt, bias, residual, out, s);
-        else if (st64 == 3) launch_tc<64, 3>(d, in, wgt, bias, residual, out, s);
+        else if (nk <= 2 || (rules ? tiles > 2 * FM_NUM_SMS : m_tiles_all >= 8 * FM_NUM_SMS))
+            launch_tc<64, 2>(d, in, wgt, bias, residual, out, s);   // OSNet 7x7 stem: 727 -> 457 us measured
         else launch_tc<64, 4>(d, in, wgt, bias, residual, out, s);
     } else {
+        // 128-wide: 6 stages = 192 KB (1 CTA / SM), 3 stages = 96 KB (2 / SM), 2 stages = 64 KB (3 / SM)
         if (nk == 1) launch_tc<128, 1>(d, in, wgt, bias, residual, out, s);
-        else if (nk <= 2) launch_tc<128, 2>(d, in, wgt, bias, residual, out, s);
-        else if (nk < 6) launch_tc<128, 3>(d, in, wgt, bias, residual, out, s);
+        else if (nk <= 2 || (rules && tiles > 2 * FM_NUM_SMS)) launch_tc<128, 2>(d, in, wgt, bias, residual, out, s);
+        else if (nk < 6 || (rules && tiles > FM_NUM_SMS)) launch_tc<128, 3>(d, in, wgt, bias, residual, out, s);
         else launch_tc<128, 6>(d, in, wgt, bias, residual, out, s);
     }
     FM_CHECK_LAUNCH("fm_conv2d_tc");
