@@ -201,10 +201,17 @@ def run_ours(args):
         peak_bw = peaks.get("hbm_gbs")
         os_ms = stage.get("osnet_ms", 0.0)
         os_gbs = stage.get("osnet_bytes", 0.0) / (os_ms * 1e-3) / 1e9 if os_ms > 0 else 0.0
+        # DRAM bytes of one OSNet forward from the committed ncu capture (dram__bytes_read + dram__bytes_write summed
+        # over the forward's kernels); null when the capture is not in the tree
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_osnet_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("osnet_forward_dram_bytes")
         out = {
             "metric": METRIC, "value": round(fps, 2), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": round(ms_dev / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "fp16 conv (fp32 accumulate), u8/fixed-point KLT, fp64 Kalman/assignment",
+            "dtype": "fp16 conv (fp32 accumulate; depthwise 3x3 sums each window row in fp16, rows in fp32), "
+                     "u8/fixed-point KLT, fp64 Kalman/assignment",
             "data": "synthetic 1920x1080 stream, 200 moving textured objects, synthetic (seeded, BN-calibrated) weights",
             "config": {"workload": WORKLOAD,
                        "streams": world, "parallelism": f"{world} independent streams, one per GPU, no collective",
@@ -220,7 +227,7 @@ def run_ours(args):
             # dominant stage of the step: the OSNet x1.0 stack on the 200 crops (1x1 tcgen05 convs + depthwise 3x3),
             # HBM bound: algorithmic bytes = every conv / depthwise layer's input + output + weights moved once
             "roofline": {"bound": "hbm", "achieved": round(os_gbs, 1), "peak": peak_bw, "unit": "GB/s",
-                         "frac": round(os_gbs / peak_bw, 4) if peak_bw else None, "traffic": None,
+                         "frac": round(os_gbs / peak_bw, 4) if peak_bw else None, "traffic": traffic,
                          "kernel": "OSNet x1.0 stack (conv_tc_kernel 1x1 + dwconv3_tile), batch 224 crops",
                          "peak_source": peak_src,
                          "bytes_per_launch": stage.get("osnet_bytes", 0.0) / max(stage.get("osnet_calls", 1), 1),
