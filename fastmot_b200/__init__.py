@@ -6,7 +6,7 @@ from .track import Track
 from .kalman_filter import KalmanFilter, MeasType
 from .flow import Flow
 from .tracker import MultiTracker, DeviceEmbeddings
-from .detector import YOLODetector, DET_DTYPE
+from .detector import YOLODetector, PublicDetector, DET_DTYPE
 from .feature_extractor import FeatureExtractor
 from .mot import MOT
 from . import models

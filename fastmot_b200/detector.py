@@ -189,3 +189,62 @@ class YOLODetector(Detector):
         dets['label'] = self._h_label.numpy()[:n]
         dets['conf'] = self._h_conf.numpy()[:n]
         return dets.view(np.recarray)
+
+
+
+class PublicDetector(Detector):
+    """MOT Challenge public detections (`det/det.txt` of a sequence directory) served at the detector cadence —
+    the reference's `PublicDetector` (fastmot/detector.py:368-431).  A file reader, not a kernel: it runs on the
+    host exactly as in the reference; everything downstream of it (ReID crops, OSNet, tracker) is the GPU path.
+
+    Row format: frame (1-based), id, left, top, width, height, conf, ... .  Each box is rounded with `to_tlbr`
+    (half-to-even on x, y, x+w-1, y+h-1), scaled from the sequence resolution (`seqinfo.ini`) to `size`, rounded
+    again, and kept if `area <= max_area`; confidences are forced to 1.0 and labels to 1 (person), as in the
+    reference.  `sequence_path` may be absolute or relative to the working directory (the reference resolves it
+    against its repository root).
+    """
+
+    def __init__(self, size, class_ids, frame_skip, sequence_path=None, conf_thresh=0.5, max_area=800000):
+        super().__init__(size)
+        import configparser
+        from collections import defaultdict
+        from pathlib import Path
+        assert tuple(class_ids) == (1,)
+        self.frame_skip = frame_skip
+        assert sequence_path is not None
+        self.seq_root = Path(sequence_path)
+        assert 0 <= conf_thresh <= 1
+        self.conf_thresh = conf_thresh
+        assert max_area >= 0
+        self.max_area = max_area
+        assert self.seq_root.exists()
+        seqinfo = configparser.ConfigParser()
+        seqinfo.read(self.seq_root / 'seqinfo.ini')
+        self.seq_size = (int(seqinfo['Sequence']['imWidth']), int(seqinfo['Sequence']['imHeight']))
+        self.detections = defaultdict(list)
+        self.frame_id = 0
+        rows = np.atleast_2d(np.loadtxt(self.seq_root / 'det' / 'det.txt', delimiter=','))
+        seq_wh = np.asarray(self.seq_size, np.float64)
+        dst_wh = np.asarray(self.size, np.float64)
+        for row in rows:
+            if row.size < 6:
+                continue
+            frame_id = int(row[0]) - 1
+            x, y, w, h = row[2:6]
+            tlbr = np.rint(np.array([x, y, x + w - 1., y + h - 1.]))       # to_tlbr, rect.py:48-57
+            tlbr[:2] = tlbr[:2] / seq_wh * dst_wh
+            tlbr[2:] = tlbr[2:] / seq_wh * dst_wh
+            tlbr = np.rint(tlbr)
+            bw, bh = tlbr[2] - tlbr[0] + 1., tlbr[3] - tlbr[1] + 1.
+            box_area = 0. if bw <= 0 or bh <= 0 else bw * bh                 # rect.py:27-32
+            conf, label = 1.0, 1
+            if conf >= self.conf_thresh and box_area <= self.max_area:
+                self.detections[frame_id].append((tlbr, label, conf))
+
+    def detect_async(self, frame):
+        pass
+
+    def postprocess(self):
+        detections = np.array(self.detections[self.frame_id], DET_DTYPE).view(np.recarray)
+        self.frame_id += self.frame_skip
+        return detections

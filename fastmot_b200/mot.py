@@ -13,7 +13,7 @@ import logging
 import numpy as np
 import torch
 
-from .detector import YOLODetector
+from .detector import YOLODetector, PublicDetector
 from .feature_extractor import FeatureExtractor
 from .tracker import MultiTracker
 from .devmem import FrameUploader
@@ -48,8 +48,8 @@ class MOT:
         self.detector_frame_skip = detector_frame_skip
         self.class_ids = tuple(np.unique(class_ids))
         self.draw = draw
-        if self.detector_type != DetectorType.YOLO:
-            raise NotImplementedError("only the YOLO detector is on the B200 hot path (SURVEY.md §2.1 row 2)")
+        if self.detector_type == DetectorType.SSD:
+            raise NotImplementedError("the SSD detector is not on the B200 hot path (SURVEY.md §2.1 row 2)")
         if yolo_detector_cfg is None:
             yolo_detector_cfg = SimpleNamespace()
         if feature_extractor_cfgs is None:
@@ -60,7 +60,14 @@ class MOT:
             raise ValueError('Number of feature extractors must match length of class IDs')
 
         LOGGER.info('Loading detector model...')
-        self.detector = YOLODetector(self.size, self.class_ids, **vars(yolo_detector_cfg))
+        if self.detector_type == DetectorType.PUBLIC:
+            if public_detector_cfg is None:
+                raise ValueError("detector_type 'PUBLIC' needs public_detector_cfg (sequence_path, conf_thresh, max_area)")
+            # mot.py:75-77: MOT Challenge public detections instead of the conv stack
+            self.detector = PublicDetector(self.size, self.class_ids, self.detector_frame_skip,
+                                           **vars(public_detector_cfg))
+        else:
+            self.detector = YOLODetector(self.size, self.class_ids, **vars(yolo_detector_cfg))
         LOGGER.info('Loading feature extractor models...')
         self.extractors = [FeatureExtractor(size=self.size, **vars(cfg)) for cfg in feature_extractor_cfgs]
         self.tracker = MultiTracker(self.size, self.extractors[0].metric, **vars(tracker_cfg),
