@@ -309,11 +309,13 @@ __device__ __forceinline__ bool staged_ok(const FmConvDesc& d, const void* resid
            (residual == nullptr || ((d.res_stride | d.res_offset) & 7) == 0);
 }
 
-template <int BN, int STAGES>
+// SPLITK instantiations carry the partial-sum path and the last-CTA reduction (they need ~135 registers; the plain
+// ones stay at 72 so that 7-8 CTAs fit on an SM for the memory-bound 1x1 layers).
+template <int BN, int STAGES, bool SPLITK>
 __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half* __restrict__ in,
                                                        const __half* __restrict__ wgt, const float* __restrict__ bias,
                                                        const __half* __restrict__ residual, __half* __restrict__ out,
-                                                       float* __restrict__ ws, int slices_per_split) {
+                                                       float* ws, int slices_per_split, int* tile_counters) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B swizzle atoms
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -466,11 +468,38 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     const int act = d.act & 0xff;
     const bool res_first = (d.act & FM_ACT_AFTER_RESIDUAL) != 0;
-    const bool staged = gridDim.z == 1 && staged_ok(d, residual);
+    const bool staged = !SPLITK && staged_ok(d, residual);
     if (staged) {
         // the ring buffers are idle now: reuse them as the staging tile
         epilogue_staged<BN>(smem + (size_t)warp * 32 * (BN * 2 + 16), lane_addr, tid & 31, m0 + warp * 32, n0, M, d,
                             bias, residual, out, act, res_first);
+    } else if (SPLITK && (d.cout & 3) == 0) {
+        // raw fp32 partials through the same smem transpose: whole rows per store instruction (the last-CTA reduction
+        // below fences on these stores, so their latency is on the critical path)
+        constexpr int PITCH = BN * 4 + 16;
+        uint8_t* stg = smem + (size_t)warp * 32 * PITCH;
+        const int lane = tid & 31;
+#pragma unroll 1
+        for (int j0 = 0; j0 < BN; j0 += 32) {
+            float v32[32];
+            tmem_ld32(lane_addr + j0, v32);
+#pragma unroll
+            for (int q = 0; q < 32; q += 4)
+                *reinterpret_cast<float4*>(stg + lane * PITCH + (j0 + q) * 4) =
+                    make_float4(v32[q], v32[q + 1], v32[q + 2], v32[q + 3]);
+        }
+        __syncwarp();
+        constexpr int LPR = BN / 4, RPI = 32 / LPR;
+        const int n = n0 + (lane % LPR) * 4;
+        float* wz = ws + (size_t)blockIdx.z * M * d.cout;
+#pragma unroll 4
+        for (int r0 = 0; r0 < 32; r0 += RPI) {
+            const int row = r0 + lane / LPR;
+            const int mm = m0 + warp * 32 + row;
+            if (mm < M && n < d.cout)
+                *reinterpret_cast<float4*>(wz + (size_t)mm * d.cout + n) =
+                    *reinterpret_cast<const float4*>(stg + row * PITCH + (lane % LPR) * 16);
+        }
     } else {
 #pragma unroll 1
         for (int j0 = 0; j0 < BN; j0 += 32) {
@@ -478,7 +507,7 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
             tmem_ld32(lane_addr + j0, v32);   // warp-collective: every lane executes it
             if (j0 == 0) DBG_STAMP(7);
             if (m >= M) continue;
-            if (gridDim.z > 1) {              // raw fp32 partials; bias / activation happen in splitk_reduce_kernel
+            if (SPLITK) {                     // raw fp32 partials; bias / activation happen in splitk_reduce_kernel
                 float* wp = ws + ((size_t)blockIdx.z * M + m) * d.cout + n0 + j0;
                 if (n0 + j0 + 32 <= d.cout && (d.cout & 7) == 0) {      // full-sector (32-byte) stores
 #pragma unroll
@@ -506,6 +535,92 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "r"((uint32_t)(BN < 32 ? 32 : BN)));
     DBG_STAMP(6);
+    // ---- split-K: the CTA that finishes a tile last sums the partials (fixed order z = 0, 1, ...: the result does
+    // not depend on arrival order) and runs the real epilogue; no separate reduce launch ----
+    if (SPLITK && tile_counters != nullptr) {
+        __shared__ int s_last;
+        __threadfence();                       // this CTA's partials are visible device-wide ...
+        __syncthreads();
+        if (tid == 0) {
+            const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+            const int ticket = atomicAdd(&tile_counters[tile], 1);     // ... before its arrival is
+            s_last = ticket == (int)gridDim.z - 1;
+            if (s_last) tile_counters[tile] = 0;                        // re-armed for the next launch
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        const size_t total = (size_t)M * d.cout;
+        const int lane = tid & 31;
+        const bool vec = ((d.cout | d.cout_stride | d.cout_offset) & 3) == 0 &&
+                         (residual == nullptr || ((d.res_stride | d.res_offset) & 3) == 0);
+        if (vec) {
+            constexpr int LPR = BN / 4;                      // lanes per row (4 columns each)
+            constexpr int RPI = 32 / LPR;                    // rows per warp instruction
+            const int n = n0 + (lane % LPR) * 4;
+            float b4[4] = {0.f, 0.f, 0.f, 0.f};
+            if (bias && n < d.cout) { b4[0] = bias[n]; b4[1] = bias[n + 1]; b4[2] = bias[n + 2]; b4[3] = bias[n + 3]; }
+            // RB rows per batch: RB x (loads of one z) are independent, so a thread keeps RB 16-byte L2 loads in flight
+            // (the one-row-at-a-time version was a chain of ~100 dependent L2 round trips and cost 20 us per tile)
+            constexpr int NR = 32 / RPI;                     // row iterations of this lane
+            constexpr int RB = NR < 16 ? NR : 16;
+#pragma unroll 1
+            for (int rb = 0; rb < NR; rb += RB) {
+                float x[RB][4];
+#pragma unroll
+                for (int j = 0; j < RB; ++j) { x[j][0] = 0.f; x[j][1] = 0.f; x[j][2] = 0.f; x[j][3] = 0.f; }
+                for (int z = 0; z < (int)gridDim.z; ++z) {
+                    float4 p4[RB];
+#pragma unroll
+                    for (int j = 0; j < RB; ++j) {
+                        const int mm = m0 + warp * 32 + (rb + j) * RPI + lane / LPR;
+                        p4[j] = (mm < M && n < d.cout)
+                                    ? __ldcg(reinterpret_cast<const float4*>(ws + (size_t)z * total + (size_t)mm * d.cout + n))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int j = 0; j < RB; ++j) { x[j][0] += p4[j].x; x[j][1] += p4[j].y; x[j][2] += p4[j].z; x[j][3] += p4[j].w; }
+                }
+#pragma unroll
+                for (int j = 0; j < RB; ++j) {
+                    const int mm = m0 + warp * 32 + (rb + j) * RPI + lane / LPR;
+                    if (mm >= M || n >= d.cout) continue;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        x[j][q] += b4[q];
+                        if (!res_first) x[j][q] = tc_act(x[j][q], act);
+                    }
+                    if (residual) {
+                        const uint2 rv = *reinterpret_cast<const uint2*>(residual + (size_t)mm * d.res_stride + d.res_offset + n);
+                        const float2 r0f = __half22float2(*reinterpret_cast<const __half2*>(&rv.x));
+                        const float2 r1f = __half22float2(*reinterpret_cast<const __half2*>(&rv.y));
+                        x[j][0] += r0f.x; x[j][1] += r0f.y; x[j][2] += r1f.x; x[j][3] += r1f.y;
+                    }
+                    if (res_first) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) x[j][q] = tc_act(x[j][q], act);
+                    }
+                    const __half2 h0 = __floats2half2_rn(x[j][0], x[j][1]), h1 = __floats2half2_rn(x[j][2], x[j][3]);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+                    pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+                    *reinterpret_cast<uint2*>(out + (size_t)mm * d.cout_stride + d.cout_offset + n) = pk;
+                }
+            }
+        } else {
+            for (int e = tid; e < TC_BM * BN; e += 128) {
+                const int mm = m0 + e / BN, n = n0 + e % BN;
+                if (mm >= M || n >= d.cout) continue;
+                float acc = 0.f;
+                for (int z = 0; z < (int)gridDim.z; ++z) acc += __ldcg(ws + (size_t)z * total + (size_t)mm * d.cout + n);
+                float v = acc + (bias ? bias[n] : 0.f);
+                if (!res_first) v = tc_act(v, act);
+                if (residual) v += __half2float(residual[(size_t)mm * d.res_stride + d.res_offset + n]);
+                if (res_first) v = tc_act(v, act);
+                out[(size_t)mm * d.cout_stride + d.cout_offset + n] = __float2half(v);
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -771,8 +886,10 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(FmConvDesc d, const 
     }
 }
 
-float* g_ws = nullptr;
+float* g_ws = nullptr;            // split-K partial sums (after the tile counters)
 long long g_ws_bytes = 0;
+int* g_tile_counters = nullptr;   // one arrival counter per output tile, zero between launches
+constexpr long long TC_COUNTER_BYTES = 4096;
 
 template <int BN, int STAGES>
 int launch_tc(const FmConvDesc* d, const void* in, const void* wgt, const float* bias, const void* residual, void* out,
@@ -780,9 +897,12 @@ int launch_tc(const FmConvDesc* d, const void* in, const void* wgt, const float*
     // the ring doubles as the epilogue's staging tile (4 warps x 32 rows x (BN*2+16) bytes)
     constexpr int ring = STAGES * (TC_BM * 128 + BN * 128), stg = 4 * 32 * (BN * 2 + 16);
     constexpr int smem = (ring > stg ? ring : stg) + 1024;
+    constexpr int stg32 = 4 * 32 * (BN * 4 + 16);       // fp32 staging of the split-K partial tile
+    constexpr int smem_split = (ring > stg32 ? ring : stg32) + 1024;
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_split);
         attr = true;
     }
     const int M = d->n * d->ho * d->wo;
@@ -791,10 +911,15 @@ int launch_tc(const FmConvDesc* d, const void* in, const void* wgt, const float*
     int sps = nk;
     // split-K when the output tiling alone cannot fill the 148 SMs (batch-1 deep layers)
     const int tiles = grid.x * grid.y;
-    if (g_ws && tiles * 2 <= FM_NUM_SMS && nk >= 8) {
+    static int split_max_tiles = -1;     // FM_CONV_SPLIT_MAXTILES overrides the largest tile count that still splits K
+    if (split_max_tiles < 0) {
+        const char* e = getenv("FM_CONV_SPLIT_MAXTILES");
+        split_max_tiles = e ? atoi(e) : FM_NUM_SMS / 2;
+    }
+    if (g_ws && tiles <= split_max_tiles && nk >= 8) {
         // as many K splits as still fit in ONE wave of resident CTAs: a 149th CTA on 148 single-CTA SMs runs after the
         // others and doubles the layer time (seen on the 40x40 and 20x20 YOLO layers: 156 / 160 CTAs, 2 waves)
-        constexpr int per_sm = (227 * 1024) / (smem + 1024) > 0 ? (227 * 1024) / (smem + 1024) : 1;
+        constexpr int per_sm = (227 * 1024) / (smem_split + 1024) > 0 ? (227 * 1024) / (smem_split + 1024) : 1;
         int want = FM_NUM_SMS * per_sm / tiles;
         if (want > nk / 4) want = nk / 4;
         if (want > 1) {
@@ -803,9 +928,21 @@ int launch_tc(const FmConvDesc* d, const void* in, const void* wgt, const float*
             if ((long long)splits * M * d->cout * 4 <= g_ws_bytes) grid.z = splits; else sps = nk;
         }
     }
-    fm_launch_pdl(conv_tc_kernel<BN, STAGES>, grid, dim3(128), (size_t)smem, s, *d, (const __half*)in,
-                  (const __half*)wgt, bias, (const __half*)residual, (__half*)out, g_ws, sps);
-    if (grid.z > 1) {
+    // FM_CONV_FUSED_REDUCE=1: the last CTA of a tile sums the partials inside the conv kernel instead of launching
+    // splitk_reduce_kernel.  Off by default: measured 80 us vs 40 us (conv + reduce kernel) on the 40x40x256->512
+    // YOLO layer; the cause (fence / single-CTA reduction latency) is not profiled yet.
+    static int fused_mode = -1;
+    if (fused_mode < 0) { const char* e = getenv("FM_CONV_FUSED_REDUCE"); fused_mode = (e && e[0] == '1') ? 1 : 0; }
+    const bool fused_reduce = fused_mode && g_tile_counters != nullptr &&
+                              tiles * (long long)sizeof(int) <= TC_COUNTER_BYTES;
+    if (grid.z > 1)
+        fm_launch_pdl(conv_tc_kernel<BN, STAGES, true>, grid, dim3(128), (size_t)smem_split, s, *d, (const __half*)in,
+                      (const __half*)wgt, bias, (const __half*)residual, (__half*)out, g_ws, sps,
+                      fused_reduce ? g_tile_counters : (int*)nullptr);
+    else
+        fm_launch_pdl(conv_tc_kernel<BN, STAGES, false>, grid, dim3(128), (size_t)smem, s, *d, (const __half*)in,
+                      (const __half*)wgt, bias, (const __half*)residual, (__half*)out, g_ws, sps, (int*)nullptr);
+    if (grid.z > 1 && !fused_reduce) {
         const size_t total = (size_t)M * d->cout;
         const int blocks = (int)((total + 255) / 256 < (size_t)FM_NUM_SMS * 8 ? (total + 255) / 256 : FM_NUM_SMS * 8);
         fm_launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), (size_t)0, s, *d, (const float*)g_ws, (int)grid.z,
@@ -824,8 +961,16 @@ extern "C" int fm_conv_set_debug(void* dbg) {
 }
 
 extern "C" int fm_conv_set_workspace(void* ws, long long bytes) {
-    g_ws = (float*)ws;
-    g_ws_bytes = bytes;
+    // layout: [tile counters, 4 KB, zeroed here and re-armed by the kernels][fp32 partial sums]
+    if (ws == nullptr || bytes <= TC_COUNTER_BYTES) {
+        g_ws = nullptr; g_ws_bytes = 0; g_tile_counters = nullptr;
+        return FM_OK;
+    }
+    cudaError_t e = cudaMemset(ws, 0, TC_COUNTER_BYTES);
+    if (e != cudaSuccess) { fm_set_last_error("fm_conv_set_workspace: cudaMemset failed"); return FM_ERR_CUDA; }
+    g_tile_counters = (int*)ws;
+    g_ws = (float*)((char*)ws + TC_COUNTER_BYTES);
+    g_ws_bytes = bytes - TC_COUNTER_BYTES;
     return FM_OK;
 }
 
