@@ -97,7 +97,8 @@ class ClockSampler:
 
 def make_frames(seed, n):
     from fastmot_b200.synth import SyntheticScene
-    scene = SyntheticScene(N_OBJECTS, seed=seed, label=0, dropout_frames=())
+    # objects bounce inside their grid cell (+-16 px): the stream holds 200 separate tracks for any number of steps
+    scene = SyntheticScene(N_OBJECTS, seed=seed, label=0, dropout_frames=(), bounce_radius=16)
     return scene, [scene.frame(t) for t in range(n)]
 
 

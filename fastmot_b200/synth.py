@@ -49,8 +49,12 @@ class SyntheticScene:
     """
 
     def __init__(self, n_objects=200, size=(1920, 1080), seed=0, label=1, emb_dim=512,
-                 pan=1, overlap=False, dropout_frames=(10, 15), dropout_every=9):
+                 pan=1, overlap=False, dropout_frames=(10, 15), dropout_every=9, bounce_radius=None):
         self.size = size
+        # bounce_radius (px): fold each object's linear displacement back into [-r, r] (triangle wave), so that a
+        # long stream keeps every object inside its grid cell -- constant track count for benchmarks of any length.
+        # None (the golden sequences) = unbounded linear motion.
+        self.bounce_radius = bounce_radius
         self.n = n_objects
         self.label = label
         self.pan = pan
@@ -79,8 +83,13 @@ class SyntheticScene:
         self.emb = emb.astype(np.float32)
 
     def positions(self, t):
-        x = np.rint(self.x0 + self.vel[:, 0] * t).astype(np.int64)
-        y = np.rint(self.y0 + self.vel[:, 1] * t).astype(np.int64)
+        dx, dy = self.vel[:, 0] * t, self.vel[:, 1] * t
+        if self.bounce_radius is not None:
+            r = float(self.bounce_radius)
+            dx = r - np.abs((dx + r) % (4 * r) - 2 * r)      # triangle wave: identity on [-r, r], period 4r
+            dy = r - np.abs((dy + r) % (4 * r) - 2 * r)
+        x = np.rint(self.x0 + dx).astype(np.int64)
+        y = np.rint(self.y0 + dy).astype(np.int64)
         return x, y
 
     def frame(self, t):
