@@ -193,7 +193,9 @@ int fm_conv2d_tc(const FmConvDesc* h_desc, const void* in, const void* wgt, cons
                  void* out, void* stream);
 int fm_conv2d_tc_supported(const FmConvDesc* h_desc);
 /* fp32 scratch for split-K (used when the 128 x BN output tiling alone cannot fill the 148 SMs, e.g. 20x20 layers at
- * batch 1); NULL disables split-K.  The caller owns the memory; convs on different streams must not split concurrently. */
+ * batch 1); NULL disables split-K.  The caller owns the memory; convs on different streams must not split concurrently.
+ * The first 4 KB hold per-tile arrival counters and are zeroed by this call (a blocking cudaMemset: call it at set-up
+ * time, not inside a stream capture); the partial sums follow. */
 int fm_conv_set_workspace(void* ws, long long bytes);
 /* Darknet maxpool (SAME_UPPER, yolo2onnx.py:838-863) with channel-slice in/out; PyTorch-style padded maxpool. */
 int fm_maxpool(const void* in, void* out, int n, int hi, int wi, int c, int cin_stride, int cin_off, int k, int stride,
