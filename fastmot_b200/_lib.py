@@ -91,6 +91,8 @@ SIGNATURES = {
     "fm_conv2d_tc_supported": (c_i, [C.POINTER(FmConvDesc)]),
     "fm_conv_set_workspace": (c_i, [c_p, c_ll]),
     "fm_dwconv3": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "fm_lite3x3": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "fm_lite3x3_supported": (c_i, [c_i, c_i, c_i, c_i]),
     "fm_global_avgpool": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p]),
     "fm_channel_gate": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "fm_fc_norm": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),

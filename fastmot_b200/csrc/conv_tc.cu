@@ -952,7 +952,285 @@ int launch_tc(const FmConvDesc* d, const void* in, const void* wgt, const float*
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fused OSNet "Lite 3x3" (torchreid LightConv3x3): y = act(dw3x3(pw1x1(x) + b_pw) + b_dw), one launch, the
+// intermediate tensor never leaves the SM.  EXPERIMENTAL (round-2 work item, opt-in through the engine with
+// FM_LITE_FUSED=1; the default path stays conv_tc_kernel + dwconv3_tile).
+//
+// One CTA owns R output rows of one image, all columns, all C channels:
+//   1. the (R + 2) x W input pixels of the strip -- one contiguous run of NHWC memory -- go to shared memory as
+//      128-pixel MMA tiles (128-byte swizzle, K slices of 64 channels); rows above / below the image are zero-filled
+//      by cp.async with size 0,
+//   2. one thread issues the tcgen05.mma for every tile (M = 128 pixels, N = C, K = cin); accumulators sit side by
+//      side in TMEM (tiles x C columns),
+//   3. all eight warps read their TMEM lanes back, add the pointwise bias, zero the rows that lie outside the image
+//      (the depthwise conv pads the POINTWISE OUTPUT with zeros, not with the bias) and write the fp16 strip into
+//      shared memory over the now idle operand tiles,
+//   4. the depthwise 3x3 runs from shared memory exactly like dwconv3_tile (fp16 row sums, fp32 across rows).
+// HBM traffic per layer: (R + 2) / R x input + output instead of 2 x input-sized round trips + output.
+// ---------------------------------------------------------------------------------------------------------
+template <int C, int NK>
+__global__ void __launch_bounds__(256) lite3x3_kernel(const __half* __restrict__ in, const __half* __restrict__ w_pw,
+                                                       const float* __restrict__ b_pw,
+                                                       const __half* __restrict__ w_dw, const float* __restrict__ b_dw,
+                                                       __half* __restrict__ out, int H, int W, int cin, int R,
+                                                       int region0_bytes, int tmem_cols, int act_dw) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int A_BYTES = TC_BM * 128, B_BYTES = C * 128;
+    constexpr int PITCH = C * 2 + 16;                       // bytes per pixel of the fp16 strip (+16: conflict-free)
+    uint8_t* sA = smem;                                     // tiles x NK slices, later the fp16 strip
+    uint8_t* sB = smem + region0_bytes;                     // NK slices of the pointwise weights
+    __half* sWd = reinterpret_cast<__half*>(sB + NK * B_BYTES);     // [9][C]
+    float* sBp = reinterpret_cast<float*>(sWd + 9 * C);              // [C] pointwise bias
+    float* sBd = sBp + C;                                            // [C] depthwise bias
+    __shared__ uint64_t bar_done;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    fm_pdl_trigger();
+    const int b = blockIdx.y, y0 = blockIdx.x * R;
+    const int P = (R + 2) * W;                              // pixels of the strip (with the two halo rows)
+    const int tiles = (P + TC_BM - 1) / TC_BM;
+    const int cch = cin >> 3;                               // 16-byte chunks per input pixel
+    if (tid == 0) {
+        mbar_init(&bar_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "r"((uint32_t)tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    // ---- weights and biases: independent of the previous kernel ----
+    for (int i = tid; i < C * NK * 8; i += blockDim.x) {
+        const int n = i / (NK * 8), cc = i - n * (NK * 8), ks = cc >> 3, c = cc & 7;
+        const int kelem = ks * TC_BK + c * 8;
+        const bool ok = kelem < cin;
+        const __half* src = ok ? w_pw + (size_t)n * cin + kelem : w_pw;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
+                         smem_u32(sB + (size_t)ks * B_BYTES + n * 128 + ((c ^ (n & 7)) << 4))),
+                     "l"(src), "r"(ok ? 16u : 0u));
+    }
+    for (int i = tid; i < 9 * C / 8; i += blockDim.x)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, 16;" ::"r"(smem_u32(sWd + (size_t)i * 8)),
+                     "l"(w_dw + (size_t)i * 8));
+    for (int i = tid; i < C; i += blockDim.x) {
+        sBp[i] = b_pw ? b_pw[i] : 0.f;
+        sBd[i] = b_dw ? b_dw[i] : 0.f;
+    }
+    fm_pdl_wait();
+    // ---- strip of the input: chunk (pixel px, 16-byte channel chunk) -> swizzled MMA tiles ----
+    const __half* img = in + (size_t)b * H * W * cin;
+    const int first = (y0 - 1) * W, npix = H * W;
+    for (int i = tid; i < tiles * TC_BM * NK * 8; i += blockDim.x) {
+        const int px = i / (NK * 8), cc = i - px * (NK * 8), ks = cc >> 3, c = cc & 7;
+        const int ch8 = ks * 8 + c, gp = first + px;
+        const bool ok = px < P && ch8 < cch && gp >= 0 && gp < npix;
+        const __half* src = ok ? img + (size_t)gp * cin + ch8 * 8 : img;
+        const int t = px >> 7, r = px & 127;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
+                         smem_u32(sA + (size_t)(t * NK + ks) * A_BYTES + r * 128 + ((c ^ (r & 7)) << 4))),
+                     "l"(src), "r"(ok ? 16u : 0u));
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem;
+    // ---- pointwise conv: tiles x NK x 4 UMMAs (128 x C x 16) ----
+    if (tid == 0) {
+        const uint32_t idesc = make_idesc(C);
+        for (int t = 0; t < tiles; ++t)
+#pragma unroll
+            for (int ks = 0; ks < NK; ++ks) {
+                const uint32_t a_addr = smem_u32(sA + (size_t)(t * NK + ks) * A_BYTES);
+                const uint32_t b_addr = smem_u32(sB + (size_t)ks * B_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k)
+                    mma_f16(tmem_base + t * C, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), idesc,
+                            (ks > 0 || k > 0) ? 1u : 0u);
+            }
+        tc_commit(&bar_done);
+    }
+    mbar_wait(&bar_done, 0);
+    tc_fence_after();
+    // ---- TMEM -> fp16 strip in shared memory (the operand tiles are dead now) ----
+    {
+        const int q = warp & 3;                              // TMEM lane quarter this warp may read
+        for (int t = warp >> 2; t < tiles; t += 2) {
+            const int px = t * TC_BM + q * 32 + lane;
+            const int gp = first + px;
+            const bool live = px < P && gp >= 0 && gp < npix;   // halo rows outside the image stay zero
+            const uint32_t taddr = tmem_base + t * C + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int j0 = 0; j0 < C; j0 += 32) {
+                float v32[32];
+                tmem_ld32(taddr + j0, v32);                  // warp-collective
+                if (px >= P) continue;
+#pragma unroll
+                for (int q0 = 0; q0 < 32; q0 += 8) {
+                    uint32_t wv[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float a = live ? v32[q0 + 2 * e] + sBp[j0 + q0 + 2 * e] : 0.f;
+                        const float c2 = live ? v32[q0 + 2 * e + 1] + sBp[j0 + q0 + 2 * e + 1] : 0.f;
+                        const __half2 h = __floats2half2_rn(a, c2);
+                        wv[e] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    *reinterpret_cast<uint4*>(sA + (size_t)px * PITCH + (j0 + q0) * 2) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols));
+    // ---- depthwise 3x3 from the strip: item = (output row, 4-pixel group, 8-channel group) ----
+    constexpr int cg = C / 8;
+    const int xg = W >> 2;
+    const int items = R * xg * cg;
+    for (int it = tid; it < items; it += blockDim.x) {
+        const int g = it % cg;
+        int t2 = it / cg;
+        const int x0 = (t2 % xg) * 4;
+        const int ry = t2 / xg;
+        const int y = y0 + ry;
+        if (y >= H) break;
+        float acc[4][8];
+#pragma unroll
+        for (int q2 = 0; q2 < 8; ++q2) {
+            const float bq = sBd[g * 8 + q2];
+#pragma unroll
+            for (int p2 = 0; p2 < 4; ++p2) acc[p2][q2] = bq;
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const uint8_t* row = sA + (size_t)((ry + r) * W) * PITCH + g * 16;
+            __half2 wv[3][4], av[6][4];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const uint4 u = *reinterpret_cast<const uint4*>(sWd + (size_t)(r * 3 + k) * C + g * 8);
+                wv[k][0] = *reinterpret_cast<const __half2*>(&u.x); wv[k][1] = *reinterpret_cast<const __half2*>(&u.y);
+                wv[k][2] = *reinterpret_cast<const __half2*>(&u.z); wv[k][3] = *reinterpret_cast<const __half2*>(&u.w);
+            }
+#pragma unroll
+            for (int cx = 0; cx < 6; ++cx) {
+                const int xx = x0 + cx - 1;
+                uint4 u = make_uint4(0u, 0u, 0u, 0u);
+                if (xx >= 0 && xx < W) u = *reinterpret_cast<const uint4*>(row + (size_t)xx * PITCH);
+                av[cx][0] = *reinterpret_cast<const __half2*>(&u.x); av[cx][1] = *reinterpret_cast<const __half2*>(&u.y);
+                av[cx][2] = *reinterpret_cast<const __half2*>(&u.z); av[cx][3] = *reinterpret_cast<const __half2*>(&u.w);
+            }
+#pragma unroll
+            for (int p2 = 0; p2 < 4; ++p2)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    __half2 sm2 = __hmul2(wv[0][j], av[p2][j]);
+                    sm2 = __hfma2(wv[1][j], av[p2 + 1][j], sm2);
+                    sm2 = __hfma2(wv[2][j], av[p2 + 2][j], sm2);
+                    const float2 f = __half22float2(sm2);
+                    acc[p2][2 * j] += f.x;
+                    acc[p2][2 * j + 1] += f.y;
+                }
+        }
+        __half* orow = out + (((size_t)b * H + y) * W + x0) * C + g * 8;
+#pragma unroll
+        for (int p2 = 0; p2 < 4; ++p2) {
+            float xv[8];
+#pragma unroll
+            for (int q2 = 0; q2 < 8; ++q2) xv[q2] = acc[p2][q2];
+            tc_act8(xv, act_dw);
+            uint32_t wv2[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const __half2 h = __floats2half2_rn(xv[2 * e], xv[2 * e + 1]);
+                wv2[e] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(orow + (size_t)p2 * C) = make_uint4(wv2[0], wv2[1], wv2[2], wv2[3]);
+        }
+    }
+}
+
+struct LitePlan { int R, tiles, region0, smem, tmem_cols; };
+
+// strip height / tile count for (H, W, C, NK): as many 128-pixel tiles as TMEM (512 columns), the 4-tile cap and
+// ~110 KB of shared memory allow, then rows balanced over the strips of an image
+inline bool lite_plan(int H, int W, int C, int NK, LitePlan* p) {
+    if (W <= 0 || (W & 3) || W > TC_BM || H <= 0) return false;
+    const int pitch = C * 2 + 16;
+    int tiles = 512 / C < 4 ? 512 / C : 4;
+    for (; tiles >= 1; --tiles) {
+        const int pmax = tiles * TC_BM;
+        int rmax = pmax / W - 2;
+        if (rmax < 1) continue;
+        if (rmax > H) rmax = H;
+        const int strips = (H + rmax - 1) / rmax;
+        const int R = (H + strips - 1) / strips;
+        const int P = (R + 2) * W;
+        const int t = (P + TC_BM - 1) / TC_BM;
+        int region0 = t * NK * TC_BM * 128;
+        if (P * pitch > region0) region0 = P * pitch;
+        region0 = (region0 + 1023) & ~1023;
+        const int smem = region0 + NK * C * 128 + 9 * C * 2 + 2 * C * 4 + 1024;
+        if (smem > 110 * 1024 && tiles > 1) continue;
+        int cols = 32;
+        while (cols < t * C) cols <<= 1;
+        if (cols > 512) continue;
+        p->R = R; p->tiles = t; p->region0 = region0; p->smem = smem; p->tmem_cols = cols;
+        return true;
+    }
+    return false;
+}
+
+template <int C, int NK>
+int launch_lite(const void* in, const void* w_pw, const float* b_pw, const void* w_dw, const float* b_dw, void* out,
+                int n, int H, int W, int cin, int act_dw, cudaStream_t s) {
+    LitePlan pl;
+    if (!lite_plan(H, W, C, NK, &pl)) return 1;
+    static int attr_bytes = 0;
+    if (pl.smem > attr_bytes) {
+        cudaFuncSetAttribute(lite3x3_kernel<C, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_bytes = 200 * 1024;
+    }
+    dim3 grid((H + pl.R - 1) / pl.R, n);
+    fm_launch_pdl(lite3x3_kernel<C, NK>, grid, dim3(256), (size_t)pl.smem, s, (const __half*)in, (const __half*)w_pw,
+                  b_pw, (const __half*)w_dw, b_dw, (__half*)out, H, W, cin, pl.R, pl.region0, pl.tmem_cols, act_dw);
+    return 0;
+}
+
 }  // namespace
+
+extern "C" int fm_lite3x3_supported(int h, int w, int cin, int c) {
+    if (cin % 8 || cin > 128 || cin < 16) return 0;
+    if (c != 32 && c != 64 && c != 96 && c != 128) return 0;
+    LitePlan pl;
+    return lite_plan(h, w, c, cin > 64 ? 2 : 1, &pl) ? 1 : 0;
+}
+
+extern "C" int fm_lite3x3(const void* in, const void* w_pw, const float* b_pw, const void* w_dw, const float* b_dw,
+                          void* out, int n, int h, int w, int cin, int c, int act_dw, void* stream) {
+    FM_REQUIRE(fm_lite3x3_supported(h, w, cin, c), "fm_lite3x3: shape not supported");
+    if (n <= 0) return FM_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = 1;
+    if (cin <= 64) {
+        if (c == 32) rc = launch_lite<32, 1>(in, w_pw, b_pw, w_dw, b_dw, out, n, h, w, cin, act_dw, s);
+        else if (c == 64) rc = launch_lite<64, 1>(in, w_pw, b_pw, w_dw, b_dw, out, n, h, w, cin, act_dw, s);
+        else if (c == 96) rc = launch_lite<96, 1>(in, w_pw, b_pw, w_dw, b_dw, out, n, h, w, cin, act_dw, s);
+        else rc = launch_lite<128, 1>(in, w_pw, b_pw, w_dw, b_dw, out, n, h, w, cin, act_dw, s);
+    } else {
+        if (c == 32) rc = launch_lite<32, 2>(in, w_pw, b_pw, w_dw, b_dw, out, n, h, w, cin, act_dw, s);
+        else if (c == 64) rc = launch_lite<64, 2>(in, w_pw, b_pw, w_dw, b_dw, out, n, h, w, cin, act_dw, s);
+        else if (c == 96) rc = launch_lite<96, 2>(in, w_pw, b_pw, w_dw, b_dw, out, n, h, w, cin, act_dw, s);
+        else rc = launch_lite<128, 2>(in, w_pw, b_pw, w_dw, b_dw, out, n, h, w, cin, act_dw, s);
+    }
+    FM_REQUIRE(rc == 0, "fm_lite3x3: no strip plan for this shape");
+    FM_CHECK_LAUNCH("fm_lite3x3");
+    return FM_OK;
+}
 
 extern "C" int fm_conv_set_debug(void* dbg) {
     unsigned long long* p = (unsigned long long*)dbg;

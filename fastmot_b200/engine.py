@@ -6,6 +6,7 @@ The launch sequence of a network is recorded once (static shapes) and replayed p
 the replay is captured into a CUDA graph so a 170-layer detector costs one launch.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -276,6 +277,10 @@ class OSNetEngine(_Net):
         self.gate_tmp = torch.zeros(4 * B, 512, dtype=torch.float32, device=dev)
         self._params = params
         fused_add = {}
+        fused_dw = {}
+        # FM_LITE_FUSED=1: run pointwise + depthwise of each Lite 3x3 as one kernel (experimental, default off)
+        self.fuse_lite = os.environ.get("FM_LITE_FUSED", "0") == "1"
+        self.n_lite = 0
         for k, op in enumerate(self.ops):
             kind = op[0]
             if kind == 'conv':
@@ -290,7 +295,22 @@ class OSNetEngine(_Net):
                 params[name] = (wd, bd)
                 y = alloc(B * ho * wo * cout)
                 nxt = self.ops[k + 1] if k + 1 < len(self.ops) else None
-                if nxt is not None and nxt[0] == 'add_relu' and nxt[1] == dst and act == 'linear' and nxt[2] in live:
+                if (self.fuse_lite and nxt is not None and nxt[0] == 'dw' and nxt[4] == dst and ks == 1
+                        and stride == 1 and pad == 0 and act == 'linear' and nxt[2] == cout
+                        and sum(dst in self._reads(o) for o in self.ops) == 1
+                        and self._lib.fm_lite3x3_supported(h, w, xc, cout)):
+                    # experimental: pointwise 1x1 + depthwise 3x3 of a Lite 3x3 block in one kernel
+                    wdw, bdw = dparam(nxt[1])
+                    wdw = wdw.half().contiguous()
+                    params[nxt[1]] = (wdw, bdw)
+                    self._add('fm_lite3x3', ptr(x), ptr(wd), ptr(bd), ptr(wdw), ptr(bdw), ptr(y), B, h, w, xc, cout,
+                              _ACT[nxt[3]])
+                    self.n_tc += 1
+                    self.n_lite += 1
+                    self.layer_bytes += 2 * (B * h * w * (xc + cout) + xc * cout + 9 * cout)
+                    fused_dw[k + 1] = True
+                    new = (nxt[5], (y, cout, h, w))
+                elif nxt is not None and nxt[0] == 'add_relu' and nxt[1] == dst and act == 'linear' and nxt[2] in live:
                     # relu(conv3(x) + identity): residual + activation in the conv epilogue, no extra pass
                     d = _conv_desc(B, h, w, xc, xc, 0, ho, wo, cout, cout, 0, ks, stride, pad,
                                    _ACT['relu'] | ACT_AFTER_RESIDUAL)
@@ -303,6 +323,8 @@ class OSNetEngine(_Net):
                     self._conv(d, x, wd, bd, y)
                     new = (dst, (y, cout, ho, wo))
             elif kind == 'dw':
+                if k in fused_dw:         # folded into the preceding pointwise conv (fm_lite3x3)
+                    continue
                 _, name, c, act, src, dst = op
                 x, xc, h, w = live[src]
                 wd, bd = dparam(name)

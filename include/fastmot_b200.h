@@ -205,7 +205,14 @@ int fm_avgpool2(const void* in, void* out, int n, int hi, int wi, int c, void* s
 /* nearest upsample (yolo2onnx.py:806-836) and/or route copy (:743-804): channel slice in -> channel slice out. */
 int fm_upsample_copy(const void* in, void* out, int n, int hi, int wi, int c, int cin_stride, int cin_off, int scale,
                      int cout_stride, int cout_off, void* stream);
-int fm_add_act(const void* a, const void* b, void* out, long long n, int act, void* stream); /* shortcut :707-731 */
+int fm_add_act(const void* a, const void* b, void* out, long long n, int act, void* stream); /* EXPERIMENTAL fused OSNet Lite 3x3 (torchreid LightConv3x3: 1x1 linear conv, then depthwise 3x3 + bias + act):
+ * out[n][h][w][c] = act(dw3x3(in[n][h][w][cin] * w_pw[c][cin] + b_pw) + b_dw), NHWC fp16, zero padding applied to the
+ * pointwise OUTPUT.  Same results as fm_conv2d_tc + fm_dwconv3 up to one fp16 rounding of the intermediate; the
+ * engine uses it only with FM_LITE_FUSED=1.  cin % 8 == 0, 16 <= cin <= 128, c in {32, 64, 96, 128}, w % 4 == 0. */
+int fm_lite3x3(const void* in, const void* w_pw, const float* b_pw, const void* w_dw, const float* b_dw, void* out,
+               int n, int h, int w, int cin, int c, int act_dw, void* stream);
+int fm_lite3x3_supported(int h, int w, int cin, int c);
+/* shortcut :707-731 */
 int fm_add_act_strided(const void* a, int a_stride, int a_off, const void* b, int b_stride, int b_off, void* out,
                        int o_stride, int o_off, long long pixels, int c, int act, void* stream);
 int fm_dwconv3(const void* in, const void* w, const float* bias, void* out, int n, int h, int wd, int c, int act,
