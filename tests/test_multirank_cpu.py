@@ -27,7 +27,7 @@ def _worker(rank, world, port, out):
 
 def test_two_ranks_track_different_streams_and_agree_on_max_time():
     world = 2
-    with mp.Manager() as m:
+    with mp.get_context("spawn").Manager() as m:      # no fork() of the multi-threaded pytest process
         out = m.dict()
         mp.spawn(_worker, args=(world, 29611, out), nprocs=world, join=True)
         r0, r1 = out[0], out[1]
