@@ -2,13 +2,23 @@
 //
 //   D[M = N*Ho*Wo pixels, Cout] = im2col(X)[M, K = kh*kw*Cin] * W^T[K, Cout],  fp16 operands, fp32 accumulate in TMEM.
 //
-// One CTA computes a 128 x BN output tile.  The K loop walks 64-element slices: all 128 threads gather the A slice
-// (128 pixels x 64 reduction elements, zero-filled at the image border) and the B slice (BN filters x 64) with 16-byte
-// cp.async (LDGSTS) copies straight into the 128-byte-swizzled K-major layout the tensor core reads; one thread
-// issues four tcgen05.mma (UMMA 128 x BN x 16) per slice and commits them to an mbarrier.  The smem ring is STAGES
-// deep with STAGES-1 slices of copies in flight, so global/L2 latency and the asynchronous MMAs overlap; a stage
-// is refilled only after the commit barrier of the MMAs that read it fired.  Epilogue: each warp reads its 32 TMEM lanes with tcgen05.ld, applies bias + activation
-// (+ residual) and stores fp16 NHWC (channel-slice aware, so route/concat layers need no copy).
+// conv_tc_kernel<BN, STAGES, SPLITK>: one CTA computes a 128 x BN output tile.  The K loop walks 64-element slices:
+// all 128 threads gather the A slice (128 pixels x 64 reduction elements, zero-filled at the image border; 1x1 /
+// stride-1 layers skip the im2col index arithmetic) and the B slice (BN filters x 64) with 16-byte cp.async (LDGSTS)
+// copies straight into the 128-byte-swizzled K-major layout the tensor core reads; one thread issues four
+// tcgen05.mma (UMMA 128 x BN x 16) per slice and commits them to an mbarrier.  The smem ring is STAGES deep with
+// STAGES-1 slices of copies in flight; a stage is refilled only after the commit barrier of the MMAs that read it
+// fired.  STAGES is chosen against the wave capacity of the layer (launch code at the bottom): deep rings for
+// one-wave layers, shallow rings (more resident CTAs) for many-wave ones.
+// Epilogue: each warp reads its 32 TMEM lanes with tcgen05.ld (one output row per thread), stages the fp16 tile in
+// the now idle ring buffers and writes it out with lanes running along the channels (row-coalesced 16-byte
+// stores), fusing bias + activation (+ residual, + channel-slice offsets, so route/concat layers need no copy).
+// Under-filled grids split K over blockIdx.z (as many splits as fit in ONE wave of resident CTAs); the partial
+// tiles go through the same smem transpose to an fp32 workspace and splitk_reduce_kernel finishes the layer.
+// All launches are programmatic-dependent-launch chains (common.cuh).
+//
+// Also here: lite3x3_kernel (experimental fused OSNet Lite 3x3, opt-in), conv_tc_smallk_kernel (persistent variant,
+// opt-in, slower) -- see profiles/r01_summary.md for the measurements behind the defaults.
 //
 // Replaces the TensorRT conv tactics behind fastmot/utils/inference.py:106-117.  Descriptor bit layouts follow the
 // PTX ISA "tcgen05 matrix / instruction descriptor" tables (cross-checked against cute/arch/mma_sm100_desc.hpp).
