@@ -8,8 +8,13 @@ from oracle.refshim import reference_available
 pytestmark = pytest.mark.skipif(not reference_available(), reason="reference tree not present")
 
 
-@pytest.mark.parametrize("scene_kw,n_frames", [(dict(n_objects=40, seed=9), 17),
-                                                (dict(n_objects=30, seed=4, overlap=True), 12)])
+@pytest.mark.parametrize("scene_kw,n_frames", [
+    (dict(n_objects=40, seed=9), 17),
+    (dict(n_objects=30, seed=4, overlap=True), 12),
+    (dict(n_objects=64, seed=1), 22),                     # config-1 size; scripted drop-outs on frames 10 / 15 -> aging,
+                                                          # IoU stage and re-identification from the history
+    (dict(n_objects=50, seed=7, bounce_radius=8), 31),    # direction reversals (benchmark scene motion model)
+])
 def test_oracle_tracker_full_pipeline_identical(scene_kw, n_frames):
     """OracleTracker + OracleFlow (cv2) vs reference MultiTracker + Flow: identical ids and boxes per frame."""
     from fastmot_b200.synth import SyntheticScene
