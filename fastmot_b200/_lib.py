@@ -39,6 +39,11 @@ class FmConvDesc(C.Structure):
                                    "res_offset")]
 
 
+class FmOsbStreams(C.Structure):
+    _fields_ = [("x", c_p), ("n", c_i), ("h", c_i), ("w", c_i), ("cin", c_i), ("mid", c_i), ("w1", c_p), ("b1", c_p),
+                ("pw", c_p), ("dw", c_p), ("tails", c_p * 4), ("gap_part", c_p)]
+
+
 class FmYoloHead(C.Structure):
     _fields_ = [("anchors", c_f * 12), ("scale_x_y", c_f)]
 
@@ -97,6 +102,9 @@ SIGNATURES = {
     "fm_channel_gate": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "fm_fc_norm": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "fm_channel_gate4": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
+    "fm_probe_umma": (c_i, [c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p]),
+    "fm_osb_streams": (c_i, [C.POINTER(FmOsbStreams), c_p]),
+    "fm_osb_streams_strips": (c_i, [c_i, c_i, c_i]),
     "fm_nms_mask_bytes": (c_ll, [c_i]),
     "fm_diou_nms_filter": (c_i, [c_p, c_p, c_p, c_i, c_d, c_d, c_d, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
 }

@@ -305,6 +305,38 @@ int fm_ransac_affine_partial_batch(const float* all_prev, const float* all_cur, 
                                    int max_iters, double confidence, double thresh, int inlier_thresh,
                                    int refine_iters, int first_round, void* stream);
 
+/* ---------------------------------------------------------------- tensor-core primitive self-test ----------- */
+/* One CTA exercises the building blocks of the fused kernels (csrc/tc_common.cuh): TMA tensor-map load of a
+ * [128 x 64] fp16 tile (rows row0.. of a [rows][64] matrix; rows past the end read as zero) into 128-byte-swizzled
+ * shared memory, cp.async.bulk of the packed weight images, tcgen05.mma with both operands in shared memory
+ * (out0 = A * B1^T, fp32 [128][n1]), tcgen05.st of the fp16-rounded result into TMEM and tcgen05.mma with A read
+ * from TMEM (out1 = fp16(out0) * B2^T, fp32 [128][n2]).  b1 / b2: K-slice images made by
+ * fastmot_b200.packing.pack_b_sw128 ([n][k] -> slices of 64 k, rows of 128 bytes, 16-byte chunks XOR-swizzled). */
+int fm_probe_umma(const void* a, int rows, int row0, const void* b1, const void* b2, int n1, int n2, float* out0,
+                  float* out1, void* stream);
+
+/* ---------------------------------------------------------------- fused OSNet OSBlock kernels --------------- */
+/* Kernel S (csrc/osnet_fused.cu): conv1 (1x1, cin -> mid, ReLU) and the four Lite-3x3 streams of one OSBlock
+ * (torchreid OSBlock.conv1 / conv2a..d; role of the TensorRT OSNet engine, fastmot/utils/inference.py:106-117) in a
+ * single launch.  x: [n][h][w][cin] fp16 NHWC; tails[s]: [n][h][w][mid] fp16 (output of stream s);
+ * gap_part: fp32 [n][strips][4][mid], the per-strip channel sums of the tails (strips = fm_osb_streams_strips()).
+ * w1: fm pack_b_sw128 image of the conv1 weights [mid][cin]; pw: ten pack_b_sw128 images [mid][mid] in the order
+ * a.0, b.0, b.1, c.0, c.1, c.2, d.0 .. d.3; dw: ten blobs { fp16 [9][mid] depthwise taps, fp32 [mid] pointwise bias,
+ * fp32 [mid] depthwise bias }.  Supported (w, mid, h): (32, 64, multiple of 8), (16, 96, 32), (8, 128, 16). */
+typedef struct FmOsbStreams {
+    const void* x;
+    int n, h, w, cin, mid;
+    const void* w1;
+    const float* b1;
+    const void* pw;
+    const void* dw;
+    void* tails[4];
+    float* gap_part;
+} FmOsbStreams;
+int fm_osb_streams(const FmOsbStreams* h_desc, void* stream);
+/* number of strips per crop kernel S uses for this geometry (0 = unsupported) */
+int fm_osb_streams_strips(int h, int w, int mid);
+
 #ifdef __cplusplus
 }
 #endif
