@@ -37,7 +37,7 @@ FRAME_SKIP = 5
 
 def _cfg():
     from types import SimpleNamespace as NS
-    from oracle.run import default_tracker_cfg   # plain data (cfg/mot.json values); no oracle compute involved
+    from fastmot_b200.config import default_tracker_cfg
     t = default_tracker_cfg()
     return dict(detector_type='YOLO', detector_frame_skip=FRAME_SKIP, class_ids=(0,),
                 yolo_detector_cfg=NS(model='YOLOv4CSP', conf_thresh=0.25, nms_thresh=0.5, max_area=800000,

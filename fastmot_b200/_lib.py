@@ -36,7 +36,7 @@ class FmTrackJob(C.Structure):
 class FmConvDesc(C.Structure):
     _fields_ = [(k, c_i) for k in ("n", "hi", "wi", "cin", "cin_stride", "cin_offset", "ho", "wo", "cout",
                                    "cout_stride", "cout_offset", "kh", "kw", "stride", "pad", "act", "res_stride",
-                                   "res_offset")]
+                                   "res_offset")] + [("ws", c_p), ("ws_bytes", c_ll)]
 
 
 class FmOsbStreams(C.Structure):
@@ -94,10 +94,7 @@ SIGNATURES = {
     "fm_add_act_strided": (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_p, c_i, c_i, c_ll, c_i, c_i, c_p]),
     "fm_conv2d_tc": (c_i, [C.POINTER(FmConvDesc), c_p, c_p, c_p, c_p, c_p, c_p]),
     "fm_conv2d_tc_supported": (c_i, [C.POINTER(FmConvDesc)]),
-    "fm_conv_set_workspace": (c_i, [c_p, c_ll]),
     "fm_dwconv3": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
-    "fm_lite3x3": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p]),
-    "fm_lite3x3_supported": (c_i, [c_i, c_i, c_i, c_i]),
     "fm_global_avgpool": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p]),
     "fm_channel_gate": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "fm_fc_norm": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
@@ -105,6 +102,8 @@ SIGNATURES = {
     "fm_probe_umma": (c_i, [c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p]),
     "fm_osb_streams": (c_i, [C.POINTER(FmOsbStreams), c_p]),
     "fm_osb_streams_strips": (c_i, [c_i, c_i, c_i]),
+    "fm_channel_gate4_pooled": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i,
+                                      c_p]),
     "fm_nms_mask_bytes": (c_ll, [c_i]),
     "fm_diou_nms_filter": (c_i, [c_p, c_p, c_p, c_i, c_d, c_d, c_d, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
 }

@@ -17,8 +17,7 @@
 // tiles go through the same smem transpose to an fp32 workspace and splitk_reduce_kernel finishes the layer.
 // All launches are programmatic-dependent-launch chains (common.cuh).
 //
-// Also here: lite3x3_kernel (experimental fused OSNet Lite 3x3, opt-in), conv_tc_smallk_kernel (persistent variant,
-// opt-in, slower) -- see profiles/r01_summary.md for the measurements behind the defaults.
+// The split-K scratch belongs to the caller (FmConvDesc.ws): one per engine / stream, no library-global state.
 //
 // Replaces the TensorRT conv tactics behind fastmot/utils/inference.py:106-117.  Descriptor bit layouts follow the
 // PTX ISA "tcgen05 matrix / instruction descriptor" tables (cross-checked against cute/arch/mma_sm100_desc.hpp).
@@ -325,7 +324,7 @@ template <int BN, int STAGES, bool SPLITK>
 __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half* __restrict__ in,
                                                        const __half* __restrict__ wgt, const float* __restrict__ bias,
                                                        const __half* __restrict__ residual, __half* __restrict__ out,
-                                                       float* ws, int slices_per_split, int* tile_counters) {
+                                                       float* ws, int slices_per_split) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B swizzle atoms
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -545,292 +544,6 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "r"((uint32_t)(BN < 32 ? 32 : BN)));
     DBG_STAMP(6);
-    // ---- split-K: the CTA that finishes a tile last sums the partials (fixed order z = 0, 1, ...: the result does
-    // not depend on arrival order) and runs the real epilogue; no separate reduce launch ----
-    if (SPLITK && tile_counters != nullptr) {
-        __shared__ int s_last;
-        __threadfence();                       // this CTA's partials are visible device-wide ...
-        __syncthreads();
-        if (tid == 0) {
-            const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-            const int ticket = atomicAdd(&tile_counters[tile], 1);     // ... before its arrival is
-            s_last = ticket == (int)gridDim.z - 1;
-            if (s_last) tile_counters[tile] = 0;                        // re-armed for the next launch
-        }
-        __syncthreads();
-        if (!s_last) return;
-        __threadfence();
-        const size_t total = (size_t)M * d.cout;
-        const int lane = tid & 31;
-        const bool vec = ((d.cout | d.cout_stride | d.cout_offset) & 3) == 0 &&
-                         (residual == nullptr || ((d.res_stride | d.res_offset) & 3) == 0);
-        if (vec) {
-            constexpr int LPR = BN / 4;                      // lanes per row (4 columns each)
-            constexpr int RPI = 32 / LPR;                    // rows per warp instruction
-            const int n = n0 + (lane % LPR) * 4;
-            float b4[4] = {0.f, 0.f, 0.f, 0.f};
-            if (bias && n < d.cout) { b4[0] = bias[n]; b4[1] = bias[n + 1]; b4[2] = bias[n + 2]; b4[3] = bias[n + 3]; }
-            // RB rows per batch: RB x (loads of one z) are independent, so a thread keeps RB 16-byte L2 loads in flight
-            // (the one-row-at-a-time version was a chain of ~100 dependent L2 round trips and cost 20 us per tile)
-            constexpr int NR = 32 / RPI;                     // row iterations of this lane
-            constexpr int RB = NR < 16 ? NR : 16;
-#pragma unroll 1
-            for (int rb = 0; rb < NR; rb += RB) {
-                float x[RB][4];
-#pragma unroll
-                for (int j = 0; j < RB; ++j) { x[j][0] = 0.f; x[j][1] = 0.f; x[j][2] = 0.f; x[j][3] = 0.f; }
-                for (int z = 0; z < (int)gridDim.z; ++z) {
-                    float4 p4[RB];
-#pragma unroll
-                    for (int j = 0; j < RB; ++j) {
-                        const int mm = m0 + warp * 32 + (rb + j) * RPI + lane / LPR;
-                        p4[j] = (mm < M && n < d.cout)
-                                    ? __ldcg(reinterpret_cast<const float4*>(ws + (size_t)z * total + (size_t)mm * d.cout + n))
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int j = 0; j < RB; ++j) { x[j][0] += p4[j].x; x[j][1] += p4[j].y; x[j][2] += p4[j].z; x[j][3] += p4[j].w; }
-                }
-#pragma unroll
-                for (int j = 0; j < RB; ++j) {
-                    const int mm = m0 + warp * 32 + (rb + j) * RPI + lane / LPR;
-                    if (mm >= M || n >= d.cout) continue;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        x[j][q] += b4[q];
-                        if (!res_first) x[j][q] = tc_act(x[j][q], act);
-                    }
-                    if (residual) {
-                        const uint2 rv = *reinterpret_cast<const uint2*>(residual + (size_t)mm * d.res_stride + d.res_offset + n);
-                        const float2 r0f = __half22float2(*reinterpret_cast<const __half2*>(&rv.x));
-                        const float2 r1f = __half22float2(*reinterpret_cast<const __half2*>(&rv.y));
-                        x[j][0] += r0f.x; x[j][1] += r0f.y; x[j][2] += r1f.x; x[j][3] += r1f.y;
-                    }
-                    if (res_first) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) x[j][q] = tc_act(x[j][q], act);
-                    }
-                    const __half2 h0 = __floats2half2_rn(x[j][0], x[j][1]), h1 = __floats2half2_rn(x[j][2], x[j][3]);
-                    uint2 pk;
-                    pk.x = *reinterpret_cast<const uint32_t*>(&h0);
-                    pk.y = *reinterpret_cast<const uint32_t*>(&h1);
-                    *reinterpret_cast<uint2*>(out + (size_t)mm * d.cout_stride + d.cout_offset + n) = pk;
-                }
-            }
-        } else {
-            for (int e = tid; e < TC_BM * BN; e += 128) {
-                const int mm = m0 + e / BN, n = n0 + e % BN;
-                if (mm >= M || n >= d.cout) continue;
-                float acc = 0.f;
-                for (int z = 0; z < (int)gridDim.z; ++z) acc += __ldcg(ws + (size_t)z * total + (size_t)mm * d.cout + n);
-                float v = acc + (bias ? bias[n] : 0.f);
-                if (!res_first) v = tc_act(v, act);
-                if (residual) v += __half2float(residual[(size_t)mm * d.res_stride + d.res_offset + n]);
-                if (res_first) v = tc_act(v, act);
-                out[(size_t)mm * d.cout_stride + d.cout_offset + n] = __float2half(v);
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Small-K persistent variant (K <= 128: the 1x1 convs of OSNet, M up to 460 k pixels).  These layers are HBM/latency
-// bound, so the per-tile fixed costs are what matter.  Each CTA keeps the weight matrix resident in smem and walks
-// tiles blockIdx.x, +gridDim.x, ...; per tile `it` the steps overlap as
-//     cp.async gather of tile it+2  |  tcgen05.mma of tile it  |  epilogue (TMEM -> smem -> HBM) of tile it-1
-// with NBUF A buffers in smem and two accumulators in TMEM.  TMEM alloc, barrier init and the weight loads are paid
-// once per CTA.
-// ---------------------------------------------------------------------------------------------------------
-template <int BN, int NK, int NBUF>
-__global__ void __launch_bounds__(128) conv_tc_smallk_kernel(FmConvDesc d, const __half* __restrict__ in,
-                                                              const __half* __restrict__ wgt,
-                                                              const float* __restrict__ bias,
-                                                              const __half* __restrict__ residual,
-                                                              __half* __restrict__ out, int m_tiles) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    constexpr int A_BYTES = TC_BM * 128, B_BYTES = BN * 128;
-    uint8_t* sB = smem;                                  // NK slices of B
-    uint8_t* sA0 = smem + NK * B_BYTES;                  // NBUF x NK slices of A
-    uint8_t* sStg = sA0 + (size_t)NBUF * NK * A_BYTES;   // 4 warps x 32 rows x (BN*2+16) bytes
-    __shared__ uint64_t bar_mma[2];
-    __shared__ uint32_t s_tmem;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n0 = blockIdx.y * BN;
-    const int M = d.n * d.ho * d.wo;
-    const int Ktot = d.kh * d.kw * d.cin;
-    if (tid == 0) {
-        mbar_init(&bar_mma[0], 1);
-        mbar_init(&bar_mma[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
-                     "r"((uint32_t)(2 * BN < 32 ? 32 : 2 * BN)));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = s_tmem;
-    const int c = tid & 7, rbase = tid >> 3;
-    const uint32_t idesc = make_idesc(BN);
-    const int n_my = (m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const bool pointwise = d.kh == 1 && d.kw == 1 && d.stride == 1 && d.pad == 0;
-
-    auto load_A = [&](int i) {                           // i-th tile of this CTA -> buffer i % NBUF
-        if (i >= n_my) return;
-        const int m0 = (blockIdx.x + i * gridDim.x) * TC_BM;
-        const int buf = i % NBUF;
-#pragma unroll
-        for (int ks = 0; ks < NK; ++ks) {
-            uint8_t* sA = sA0 + (size_t)(buf * NK + ks) * A_BYTES;
-            const int kelem = ks * TC_BK + c * 8;
-            const bool kvalid = kelem < Ktot;
-            if (pointwise) {
-                const __half* base = in + d.cin_offset + (kvalid ? kelem : 0);
-#pragma unroll
-                for (int i2 = 0; i2 < 8; ++i2) {
-                    const int r = rbase + 16 * i2;
-                    const bool ok = kvalid && m0 + r < M;
-                    const __half* src = ok ? base + (size_t)(m0 + r) * d.cin_stride : in;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
-                                     smem_u32(sA + r * 128 + ((c ^ (r & 7)) << 4))),
-                                 "l"(src), "r"(ok ? 16u : 0u));
-                }
-                continue;
-            }
-            const int tap = kvalid ? kelem / d.cin : 0;
-            const int cch = kvalid ? kelem - tap * d.cin : 0;
-            const int fr = tap / d.kw, fs = tap - fr * d.kw;
-#pragma unroll
-            for (int i2 = 0; i2 < 8; ++i2) {
-                const int r = rbase + 16 * i2;
-                const int m = m0 + r;
-                const __half* src = in;
-                uint32_t bytes = 0;
-                if (kvalid && m < M) {
-                    const int wo = m % d.wo, t = m / d.wo, ho = t % d.ho, nb = t / d.ho;
-                    const int hi = ho * d.stride - d.pad + fr, wi = wo * d.stride - d.pad + fs;
-                    if (hi >= 0 && hi < d.hi && wi >= 0 && wi < d.wi) {
-                        src = in + (((size_t)nb * d.hi + hi) * d.wi + wi) * d.cin_stride + d.cin_offset + cch;
-                        bytes = 16;
-                    }
-                }
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
-                                 smem_u32(sA + r * 128 + ((c ^ (r & 7)) << 4))),
-                             "l"(src), "r"(bytes));
-            }
-        }
-    };
-    // weights: resident for the whole CTA (same cp.async group as the first A tile)
-#pragma unroll
-    for (int ks = 0; ks < NK; ++ks) {
-        const int kelem = ks * TC_BK + c * 8;
-#pragma unroll
-        for (int i = 0; i < BN / 16; ++i) {
-            const int r = rbase + 16 * i;
-            const int n = n0 + r;
-            const bool ok = kelem < Ktot && n < d.cout;
-            const __half* src = ok ? wgt + (size_t)n * Ktot + kelem : wgt;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
-                             smem_u32(sB + (size_t)ks * B_BYTES + r * 128 + ((c ^ (r & 7)) << 4))),
-                         "l"(src), "r"(ok ? 16u : 0u));
-        }
-    }
-    // prologue: NBUF-1 tiles in flight
-#pragma unroll
-    for (int i = 0; i < NBUF - 1; ++i) {
-        load_A(i);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    const int act = d.act & 0xff;
-    const bool res_first = (d.act & FM_ACT_AFTER_RESIDUAL) != 0;
-    const bool staged = staged_ok(d, residual);
-    uint8_t* stg = sStg + (size_t)warp * 32 * (BN * 2 + 16);
-
-    auto epilogue = [&](int j) {                         // accumulator j & 1 -> HBM (its MMAs are known complete)
-        const int m0 = (blockIdx.x + j * gridDim.x) * TC_BM;
-        const uint32_t lane_addr = tmem_base + (j & 1) * BN + ((uint32_t)(warp * 32) << 16);
-        if (staged) {
-            epilogue_staged<BN>(stg, lane_addr, lane, m0 + warp * 32, n0, M, d, bias, residual, out, act, res_first);
-        } else {
-            const int m = m0 + tid;
-#pragma unroll 1
-            for (int j0 = 0; j0 < BN; j0 += 32) {
-                float v32[32];
-                tmem_ld32(lane_addr + j0, v32);
-                if (m >= M) continue;
-                epilogue_store32(v32, (size_t)m, n0 + j0, d, bias, residual, out, act, res_first);
-            }
-        }
-    };
-
-    for (int it = 0; it < n_my; ++it) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(NBUF - 2) : "memory");   // tile `it` has landed (this thread)
-        fence_async_smem();
-        tc_fence_before();       // orders the TMEM reads of epilogue(it-2) before the MMAs that reuse that accumulator
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            const int buf = it % NBUF;
-#pragma unroll
-            for (int ks = 0; ks < NK; ++ks) {
-                const uint32_t a_addr = smem_u32(sA0 + (size_t)(buf * NK + ks) * A_BYTES);
-                const uint32_t b_addr = smem_u32(sB + (size_t)ks * B_BYTES);
-#pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k)
-                    mma_f16(tmem_base + (it & 1) * BN, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32),
-                            idesc, (ks > 0 || k > 0) ? 1u : 0u);
-            }
-            tc_commit(&bar_mma[it & 1]);
-        }
-        if (it > 0) {
-            // MMAs of tile it-1 done => its accumulator is readable and its A buffer ((it-1) % NBUF) is free
-            mbar_wait(&bar_mma[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) & 1));
-            tc_fence_after();
-        }
-        load_A(it + NBUF - 1);                           // lands in buffer (it-1) % NBUF
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        if (it > 0) epilogue(it - 1);
-    }
-    if (n_my > 0) {
-        const int j = n_my - 1;
-        mbar_wait(&bar_mma[j & 1], (uint32_t)((j >> 1) & 1));
-        tc_fence_after();
-        epilogue(j);
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                     "r"((uint32_t)(2 * BN < 32 ? 32 : 2 * BN)));
-}
-
-template <int BN, int NK, int NBUF>
-int launch_tc_smallk(const FmConvDesc* d, const void* in, const void* wgt, const float* bias, const void* residual,
-                     void* out, cudaStream_t s) {
-    constexpr int smem = NK * BN * 128 + NBUF * NK * TC_BM * 128 + 4 * 32 * (BN * 2 + 16) + 1024;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(conv_tc_smallk_kernel<BN, NK, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr = true;
-    }
-    const int M = d->n * d->ho * d->wo;
-    const int m_tiles = fm_cdiv(M, TC_BM);
-    const int n_tiles = fm_cdiv(d->cout, BN);
-    int per_sm = (226 * 1024) / (smem + 1024);        // shared-memory limit (1 KB per CTA is reserved by the driver)
-    if (per_sm > 512 / (2 * BN)) per_sm = 512 / (2 * BN);   // TMEM limit: two BN-column accumulators per CTA
-    if (per_sm > 4) per_sm = 4;
-    if (per_sm < 1) per_sm = 1;
-    int gx = FM_NUM_SMS * per_sm / n_tiles;
-    if (gx < 1) gx = 1;
-    if (gx > m_tiles) gx = m_tiles;
-    dim3 grid(gx, n_tiles, 1);
-    conv_tc_smallk_kernel<BN, NK, NBUF><<<grid, 128, smem, s>>>(*d, (const __half*)in, (const __half*)wgt, bias,
-                                                                (const __half*)residual, (__half*)out, m_tiles);
-    return 0;
 }
 
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(FmConvDesc d, const float* __restrict__ ws, int splits,
@@ -896,11 +609,6 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(FmConvDesc d, const 
     }
 }
 
-float* g_ws = nullptr;            // split-K partial sums (after the tile counters)
-long long g_ws_bytes = 0;
-int* g_tile_counters = nullptr;   // one arrival counter per output tile, zero between launches
-constexpr long long TC_COUNTER_BYTES = 4096;
-
 template <int BN, int STAGES>
 int launch_tc(const FmConvDesc* d, const void* in, const void* wgt, const float* bias, const void* residual, void* out,
               cudaStream_t s) {
@@ -926,7 +634,8 @@ int launch_tc(const FmConvDesc* d, const void* in, const void* wgt, const float*
         const char* e = getenv("FM_CONV_SPLIT_MAXTILES");
         split_max_tiles = e ? atoi(e) : FM_NUM_SMS / 2;
     }
-    if (g_ws && tiles <= split_max_tiles && nk >= 8) {
+    float* ws = (float*)d->ws;
+    if (ws && tiles <= split_max_tiles && nk >= 8) {
         // as many K splits as still fit in ONE wave of resident CTAs: a 149th CTA on 148 single-CTA SMs runs after the
         // others and doubles the layer time (seen on the 40x40 and 20x20 YOLO layers: 156 / 160 CTAs, 2 waves)
         constexpr int per_sm = (227 * 1024) / (smem_split + 1024) > 0 ? (227 * 1024) / (smem_split + 1024) : 1;
@@ -935,330 +644,30 @@ int launch_tc(const FmConvDesc* d, const void* in, const void* wgt, const float*
         if (want > 1) {
             sps = (nk + want - 1) / want;
             const int splits = (nk + sps - 1) / sps;
-            if ((long long)splits * M * d->cout * 4 <= g_ws_bytes) grid.z = splits; else sps = nk;
+            if ((long long)splits * M * d->cout * 4 <= d->ws_bytes) grid.z = splits; else sps = nk;
         }
     }
-    // FM_CONV_FUSED_REDUCE=1: the last CTA of a tile sums the partials inside the conv kernel instead of launching
-    // splitk_reduce_kernel.  Off by default: measured 80 us vs 40 us (conv + reduce kernel) on the 40x40x256->512
-    // YOLO layer; the cause (fence / single-CTA reduction latency) is not profiled yet.
-    static int fused_mode = -1;
-    if (fused_mode < 0) { const char* e = getenv("FM_CONV_FUSED_REDUCE"); fused_mode = (e && e[0] == '1') ? 1 : 0; }
-    const bool fused_reduce = fused_mode && g_tile_counters != nullptr &&
-                              tiles * (long long)sizeof(int) <= TC_COUNTER_BYTES;
     if (grid.z > 1)
         fm_launch_pdl(conv_tc_kernel<BN, STAGES, true>, grid, dim3(128), (size_t)smem_split, s, *d, (const __half*)in,
-                      (const __half*)wgt, bias, (const __half*)residual, (__half*)out, g_ws, sps,
-                      fused_reduce ? g_tile_counters : (int*)nullptr);
+                      (const __half*)wgt, bias, (const __half*)residual, (__half*)out, ws, sps);
     else
         fm_launch_pdl(conv_tc_kernel<BN, STAGES, false>, grid, dim3(128), (size_t)smem, s, *d, (const __half*)in,
-                      (const __half*)wgt, bias, (const __half*)residual, (__half*)out, g_ws, sps, (int*)nullptr);
-    if (grid.z > 1 && !fused_reduce) {
+                      (const __half*)wgt, bias, (const __half*)residual, (__half*)out, ws, sps);
+    if (grid.z > 1) {
         const size_t total = (size_t)M * d->cout;
         const int blocks = (int)((total + 255) / 256 < (size_t)FM_NUM_SMS * 8 ? (total + 255) / 256 : FM_NUM_SMS * 8);
-        fm_launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), (size_t)0, s, *d, (const float*)g_ws, (int)grid.z,
+        fm_launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), (size_t)0, s, *d, (const float*)ws, (int)grid.z,
                       bias, (const __half*)residual, (__half*)out);
         fm_count_launches(1);
     }
     return 0;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Fused OSNet "Lite 3x3" (torchreid LightConv3x3): y = act(dw3x3(pw1x1(x) + b_pw) + b_dw), one launch, the
-// intermediate tensor never leaves the SM.  EXPERIMENTAL (round-2 work item, opt-in through the engine with
-// FM_LITE_FUSED=1; the default path stays conv_tc_kernel + dwconv3_tile).
-//
-// One CTA owns R output rows of one image, all columns, all C channels:
-//   1. the (R + 2) x W input pixels of the strip -- one contiguous run of NHWC memory -- go to shared memory as
-//      128-pixel MMA tiles (128-byte swizzle, K slices of 64 channels); rows above / below the image are zero-filled
-//      by cp.async with size 0,
-//   2. one thread issues the tcgen05.mma for every tile (M = 128 pixels, N = C, K = cin); accumulators sit side by
-//      side in TMEM (tiles x C columns),
-//   3. all eight warps read their TMEM lanes back, add the pointwise bias, zero the rows that lie outside the image
-//      (the depthwise conv pads the POINTWISE OUTPUT with zeros, not with the bias) and write the fp16 strip into
-//      shared memory over the now idle operand tiles,
-//   4. the depthwise 3x3 runs from shared memory exactly like dwconv3_tile (fp16 row sums, fp32 across rows).
-// HBM traffic per layer: (R + 2) / R x input + output instead of 2 x input-sized round trips + output.
-// ---------------------------------------------------------------------------------------------------------
-template <int C, int NK>
-__global__ void __launch_bounds__(256) lite3x3_kernel(const __half* __restrict__ in, const __half* __restrict__ w_pw,
-                                                       const float* __restrict__ b_pw,
-                                                       const __half* __restrict__ w_dw, const float* __restrict__ b_dw,
-                                                       __half* __restrict__ out, int H, int W, int cin, int R,
-                                                       int region0_bytes, int tmem_cols, int act_dw) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    constexpr int A_BYTES = TC_BM * 128, B_BYTES = C * 128;
-    constexpr int PITCH = C * 2 + 16;                       // bytes per pixel of the fp16 strip (+16: conflict-free)
-    uint8_t* sA = smem;                                     // tiles x NK slices, later the fp16 strip
-    uint8_t* sB = smem + region0_bytes;                     // NK slices of the pointwise weights
-    __half* sWd = reinterpret_cast<__half*>(sB + NK * B_BYTES);     // [9][C]
-    float* sBp = reinterpret_cast<float*>(sWd + 9 * C);              // [C] pointwise bias
-    float* sBd = sBp + C;                                            // [C] depthwise bias
-    __shared__ uint64_t bar_done;
-    __shared__ uint32_t s_tmem;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    fm_pdl_trigger();
-    const int b = blockIdx.y, y0 = blockIdx.x * R;
-    const int P = (R + 2) * W;                              // pixels of the strip (with the two halo rows)
-    const int tiles = (P + TC_BM - 1) / TC_BM;
-    const int cch = cin >> 3;                               // 16-byte chunks per input pixel
-    if (tid == 0) {
-        mbar_init(&bar_done, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
-                     "r"((uint32_t)tmem_cols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    // ---- weights and biases: independent of the previous kernel ----
-    for (int i = tid; i < C * NK * 8; i += blockDim.x) {
-        const int n = i / (NK * 8), cc = i - n * (NK * 8), ks = cc >> 3, c = cc & 7;
-        const int kelem = ks * TC_BK + c * 8;
-        const bool ok = kelem < cin;
-        const __half* src = ok ? w_pw + (size_t)n * cin + kelem : w_pw;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
-                         smem_u32(sB + (size_t)ks * B_BYTES + n * 128 + ((c ^ (n & 7)) << 4))),
-                     "l"(src), "r"(ok ? 16u : 0u));
-    }
-    for (int i = tid; i < 9 * C / 8; i += blockDim.x)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, 16;" ::"r"(smem_u32(sWd + (size_t)i * 8)),
-                     "l"(w_dw + (size_t)i * 8));
-    for (int i = tid; i < C; i += blockDim.x) {
-        sBp[i] = b_pw ? b_pw[i] : 0.f;
-        sBd[i] = b_dw ? b_dw[i] : 0.f;
-    }
-    fm_pdl_wait();
-    // ---- strip of the input: chunk (pixel px, 16-byte channel chunk) -> swizzled MMA tiles ----
-    const __half* img = in + (size_t)b * H * W * cin;
-    const int first = (y0 - 1) * W, npix = H * W;
-    for (int i = tid; i < tiles * TC_BM * NK * 8; i += blockDim.x) {
-        const int px = i / (NK * 8), cc = i - px * (NK * 8), ks = cc >> 3, c = cc & 7;
-        const int ch8 = ks * 8 + c, gp = first + px;
-        const bool ok = px < P && ch8 < cch && gp >= 0 && gp < npix;
-        const __half* src = ok ? img + (size_t)gp * cin + ch8 * 8 : img;
-        const int t = px >> 7, r = px & 127;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
-                         smem_u32(sA + (size_t)(t * NK + ks) * A_BYTES + r * 128 + ((c ^ (r & 7)) << 4))),
-                     "l"(src), "r"(ok ? 16u : 0u));
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = s_tmem;
-    // ---- pointwise conv: tiles x NK x 4 UMMAs (128 x C x 16) ----
-    if (tid == 0) {
-        const uint32_t idesc = make_idesc(C);
-        for (int t = 0; t < tiles; ++t)
-#pragma unroll
-            for (int ks = 0; ks < NK; ++ks) {
-                const uint32_t a_addr = smem_u32(sA + (size_t)(t * NK + ks) * A_BYTES);
-                const uint32_t b_addr = smem_u32(sB + (size_t)ks * B_BYTES);
-#pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k)
-                    mma_f16(tmem_base + t * C, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), idesc,
-                            (ks > 0 || k > 0) ? 1u : 0u);
-            }
-        tc_commit(&bar_done);
-    }
-    mbar_wait(&bar_done, 0);
-    tc_fence_after();
-    // ---- TMEM -> fp16 strip in shared memory (the operand tiles are dead now) ----
-    {
-        const int q = warp & 3;                              // TMEM lane quarter this warp may read
-        for (int t = warp >> 2; t < tiles; t += 2) {
-            const int px = t * TC_BM + q * 32 + lane;
-            const int gp = first + px;
-            const bool live = px < P && gp >= 0 && gp < npix;   // halo rows outside the image stay zero
-            const uint32_t taddr = tmem_base + t * C + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-            for (int j0 = 0; j0 < C; j0 += 32) {
-                float v32[32];
-                tmem_ld32(taddr + j0, v32);                  // warp-collective
-                if (px >= P) continue;
-#pragma unroll
-                for (int q0 = 0; q0 < 32; q0 += 8) {
-                    uint32_t wv[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float a = live ? v32[q0 + 2 * e] + sBp[j0 + q0 + 2 * e] : 0.f;
-                        const float c2 = live ? v32[q0 + 2 * e + 1] + sBp[j0 + q0 + 2 * e + 1] : 0.f;
-                        const __half2 h = __floats2half2_rn(a, c2);
-                        wv[e] = *reinterpret_cast<const uint32_t*>(&h);
-                    }
-                    *reinterpret_cast<uint4*>(sA + (size_t)px * PITCH + (j0 + q0) * 2) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols));
-    // ---- depthwise 3x3 from the strip: item = (output row, 4-pixel group, 8-channel group) ----
-    constexpr int cg = C / 8;
-    const int xg = W >> 2;
-    const int items = R * xg * cg;
-    for (int it = tid; it < items; it += blockDim.x) {
-        const int g = it % cg;
-        int t2 = it / cg;
-        const int x0 = (t2 % xg) * 4;
-        const int ry = t2 / xg;
-        const int y = y0 + ry;
-        if (y >= H) break;
-        float acc[4][8];
-#pragma unroll
-        for (int q2 = 0; q2 < 8; ++q2) {
-            const float bq = sBd[g * 8 + q2];
-#pragma unroll
-            for (int p2 = 0; p2 < 4; ++p2) acc[p2][q2] = bq;
-        }
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const uint8_t* row = sA + (size_t)((ry + r) * W) * PITCH + g * 16;
-            __half2 wv[3][4], av[6][4];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const uint4 u = *reinterpret_cast<const uint4*>(sWd + (size_t)(r * 3 + k) * C + g * 8);
-                wv[k][0] = *reinterpret_cast<const __half2*>(&u.x); wv[k][1] = *reinterpret_cast<const __half2*>(&u.y);
-                wv[k][2] = *reinterpret_cast<const __half2*>(&u.z); wv[k][3] = *reinterpret_cast<const __half2*>(&u.w);
-            }
-#pragma unroll
-            for (int cx = 0; cx < 6; ++cx) {
-                const int xx = x0 + cx - 1;
-                uint4 u = make_uint4(0u, 0u, 0u, 0u);
-                if (xx >= 0 && xx < W) u = *reinterpret_cast<const uint4*>(row + (size_t)xx * PITCH);
-                av[cx][0] = *reinterpret_cast<const __half2*>(&u.x); av[cx][1] = *reinterpret_cast<const __half2*>(&u.y);
-                av[cx][2] = *reinterpret_cast<const __half2*>(&u.z); av[cx][3] = *reinterpret_cast<const __half2*>(&u.w);
-            }
-#pragma unroll
-            for (int p2 = 0; p2 < 4; ++p2)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    __half2 sm2 = __hmul2(wv[0][j], av[p2][j]);
-                    sm2 = __hfma2(wv[1][j], av[p2 + 1][j], sm2);
-                    sm2 = __hfma2(wv[2][j], av[p2 + 2][j], sm2);
-                    const float2 f = __half22float2(sm2);
-                    acc[p2][2 * j] += f.x;
-                    acc[p2][2 * j + 1] += f.y;
-                }
-        }
-        __half* orow = out + (((size_t)b * H + y) * W + x0) * C + g * 8;
-#pragma unroll
-        for (int p2 = 0; p2 < 4; ++p2) {
-            float xv[8];
-#pragma unroll
-            for (int q2 = 0; q2 < 8; ++q2) xv[q2] = acc[p2][q2];
-            tc_act8(xv, act_dw);
-            uint32_t wv2[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const __half2 h = __floats2half2_rn(xv[2 * e], xv[2 * e + 1]);
-                wv2[e] = *reinterpret_cast<const uint32_t*>(&h);
-            }
-            *reinterpret_cast<uint4*>(orow + (size_t)p2 * C) = make_uint4(wv2[0], wv2[1], wv2[2], wv2[3]);
-        }
-    }
-}
-
-struct LitePlan { int R, tiles, region0, smem, tmem_cols; };
-
-// strip height / tile count for (H, W, C, NK): as many 128-pixel tiles as TMEM (512 columns), the 4-tile cap and
-// ~110 KB of shared memory allow, then rows balanced over the strips of an image
-inline bool lite_plan(int H, int W, int C, int NK, LitePlan* p) {
-    if (W <= 0 || (W & 3) || W > TC_BM || H <= 0) return false;
-    const int pitch = C * 2 + 16;
-    int tiles = 512 / C < 4 ? 512 / C : 4;
-    for (; tiles >= 1; --tiles) {
-        const int pmax = tiles * TC_BM;
-        int rmax = pmax / W - 2;
-        if (rmax < 1) continue;
-        if (rmax > H) rmax = H;
-        const int strips = (H + rmax - 1) / rmax;
-        const int R = (H + strips - 1) / strips;
-        const int P = (R + 2) * W;
-        const int t = (P + TC_BM - 1) / TC_BM;
-        int region0 = t * NK * TC_BM * 128;
-        if (P * pitch > region0) region0 = P * pitch;
-        region0 = (region0 + 1023) & ~1023;
-        const int smem = region0 + NK * C * 128 + 9 * C * 2 + 2 * C * 4 + 1024;
-        if (smem > 110 * 1024 && tiles > 1) continue;
-        int cols = 32;
-        while (cols < t * C) cols <<= 1;
-        if (cols > 512) continue;
-        p->R = R; p->tiles = t; p->region0 = region0; p->smem = smem; p->tmem_cols = cols;
-        return true;
-    }
-    return false;
-}
-
-template <int C, int NK>
-int launch_lite(const void* in, const void* w_pw, const float* b_pw, const void* w_dw, const float* b_dw, void* out,
-                int n, int H, int W, int cin, int act_dw, cudaStream_t s) {
-    LitePlan pl;
-    if (!lite_plan(H, W, C, NK, &pl)) return 1;
-    static int attr_bytes = 0;
-    if (pl.smem > attr_bytes) {
-        cudaFuncSetAttribute(lite3x3_kernel<C, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_bytes = 200 * 1024;
-    }
-    dim3 grid((H + pl.R - 1) / pl.R, n);
-    fm_launch_pdl(lite3x3_kernel<C, NK>, grid, dim3(256), (size_t)pl.smem, s, (const __half*)in, (const __half*)w_pw,
-                  b_pw, (const __half*)w_dw, b_dw, (__half*)out, H, W, cin, pl.R, pl.region0, pl.tmem_cols, act_dw);
-    return 0;
-}
-
 }  // namespace
-
-extern "C" int fm_lite3x3_supported(int h, int w, int cin, int c) {
-    if (cin % 8 || cin > 128 || cin < 16) return 0;
-    if (c != 32 && c != 64 && c != 96 && c != 128) return 0;
-    LitePlan pl;
-    return lite_plan(h, w, c, cin > 64 ? 2 : 1, &pl) ? 1 : 0;
-}
-
-extern "C" int fm_lite3x3(const void* in, const void* w_pw, const float* b_pw, const void* w_dw, const float* b_dw,
-                          void* out, int n, int h, int w, int cin, int c, int act_dw, void* stream) {
-    FM_REQUIRE(fm_lite3x3_supported(h, w, cin, c), "fm_lite3x3: shape not supported");
-    if (n <= 0) return FM_OK;
-    cudaStream_t s = (cudaStream_t)stream;
-    int rc = 1;
-    if (cin <= 64) {
-        if (c == 32) rc = launch_lite<32, 1>(in, w_pw, b_pw, w_dw, b_dw, out, n, h, w, cin, act_dw, s);
-        else if (c == 64) rc = launch_lite<64, 1>(in, w_pw, b_pw, w_dw, b_dw, out, n, h, w, cin, act_dw, s);
-        else if (c == 96) rc = launch_lite<96, 1>(in, w_pw, b_pw, w_dw, b_dw, out, n, h, w, cin, act_dw, s);
-        else rc = launch_lite<128, 1>(in, w_pw, b_pw, w_dw, b_dw, out, n, h, w, cin, act_dw, s);
-    } else {
-        if (c == 32) rc = launch_lite<32, 2>(in, w_pw, b_pw, w_dw, b_dw, out, n, h, w, cin, act_dw, s);
-        else if (c == 64) rc = launch_lite<64, 2>(in, w_pw, b_pw, w_dw, b_dw, out, n, h, w, cin, act_dw, s);
-        else if (c == 96) rc = launch_lite<96, 2>(in, w_pw, b_pw, w_dw, b_dw, out, n, h, w, cin, act_dw, s);
-        else rc = launch_lite<128, 2>(in, w_pw, b_pw, w_dw, b_dw, out, n, h, w, cin, act_dw, s);
-    }
-    FM_REQUIRE(rc == 0, "fm_lite3x3: no strip plan for this shape");
-    FM_CHECK_LAUNCH("fm_lite3x3");
-    return FM_OK;
-}
 
 extern "C" int fm_conv_set_debug(void* dbg) {
     unsigned long long* p = (unsigned long long*)dbg;
     cudaMemcpyToSymbol(g_dbg_dev, &p, sizeof(p));
-    return FM_OK;
-}
-
-extern "C" int fm_conv_set_workspace(void* ws, long long bytes) {
-    // layout: [tile counters, 4 KB, zeroed here and re-armed by the kernels][fp32 partial sums]
-    if (ws == nullptr || bytes <= TC_COUNTER_BYTES) {
-        g_ws = nullptr; g_ws_bytes = 0; g_tile_counters = nullptr;
-        return FM_OK;
-    }
-    cudaError_t e = cudaMemset(ws, 0, TC_COUNTER_BYTES);
-    if (e != cudaSuccess) { fm_set_last_error("fm_conv_set_workspace: cudaMemset failed"); return FM_ERR_CUDA; }
-    g_tile_counters = (int*)ws;
-    g_ws = (float*)((char*)ws + TC_COUNTER_BYTES);
-    g_ws_bytes = bytes - TC_COUNTER_BYTES;
     return FM_OK;
 }
 
@@ -1277,25 +686,6 @@ extern "C" int fm_conv2d_tc(const FmConvDesc* d, const void* in, const void* wgt
     cudaStream_t s = (cudaStream_t)stream;
     const int nk = (d->kh * d->kw * d->cin + TC_BK - 1) / TC_BK;
     const int m_tiles_all = (d->n * d->ho * d->wo + TC_BM - 1) / TC_BM;
-    static int smallk_mode = -1;   // FM_CONV_SMALLK=1 enables the persistent small-K variant (experimental)
-    if (smallk_mode < 0) {
-        const char* e = getenv("FM_CONV_SMALLK");
-        smallk_mode = (e && e[0] == '1') ? 1 : 0;   // measured slower than the tile-per-CTA kernel: off by default
-    }
-    if (smallk_mode && nk <= 2 && m_tiles_all >= 4 * FM_NUM_SMS) {      // big-M, tiny-K: persistent variant
-        if (d->cout <= 32) {
-            if (nk == 1) launch_tc_smallk<32, 1, 3>(d, in, wgt, bias, residual, out, s);
-            else launch_tc_smallk<32, 2, 3>(d, in, wgt, bias, residual, out, s);
-        } else if (d->cout <= 64) {
-            if (nk == 1) launch_tc_smallk<64, 1, 3>(d, in, wgt, bias, residual, out, s);
-            else launch_tc_smallk<64, 2, 3>(d, in, wgt, bias, residual, out, s);
-        } else {
-            if (nk == 1) launch_tc_smallk<128, 1, 3>(d, in, wgt, bias, residual, out, s);
-            else launch_tc_smallk<128, 2, 3>(d, in, wgt, bias, residual, out, s);
-        }
-        FM_CHECK_LAUNCH("fm_conv2d_tc(smallk)");
-        return FM_OK;
-    }
     // ring depth follows the K extent: short reductions (OSNet 1x1) want many co-resident CTAs, long ones (3x3 on
     // wide layers) want many slices of copies in flight
     static int force_bn = -1;      // FM_CONV_BN=32|64|128 overrides the tile width (experiments only)

@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(128) lk_kernel(FmPyramid prev, FmPyramid cur, 
                     }
                 }
                 ev = group_sum(ev);
-                if (err_on) err = ev * (1.f / (32 * win_w * win_h));
+                if (err_on) err = ev / (float)(32 * win_w * win_h);   // OpenCV divides (1-ulp difference from a reciprocal)
             }
         }
         if (valid && lane8 == 0) {

@@ -558,6 +558,57 @@ __global__ void __launch_bounds__(256) gate_apply4_vec(Ptr4 x, const float* __re
 
 }  // namespace
 
+namespace {
+// gate FCs fed by the per-strip channel sums fm_osb_streams leaves behind (no separate pooling pass)
+__global__ void __launch_bounds__(128) gate_fc4_part_kernel(const float* __restrict__ gap_part, int strips, int n, int hw,
+                                                             const float* __restrict__ w1, const float* __restrict__ b1,
+                                                             const float* __restrict__ w2, const float* __restrict__ b2,
+                                                             float* __restrict__ gate, int c, int cr) {
+    extern __shared__ float sh[];
+    float* sp = sh;
+    float* sh1 = sh + c;
+    const int st = blockIdx.x / n, b = blockIdx.x - st * n;
+    const float inv = 1.f / (float)hw;
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+        float a = 0.f;
+        for (int k = 0; k < strips; ++k) a += gap_part[(((size_t)b * strips + k) * 4 + st) * c + i];
+        sp[i] = a * inv;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < cr; j += blockDim.x) {
+        float a = b1[j];
+        for (int i = 0; i < c; ++i) a += w1[(size_t)j * c + i] * sp[i];
+        sh1[j] = a > 0.f ? a : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+        float a = b2[i];
+        for (int j = 0; j < cr; ++j) a += w2[(size_t)i * cr + j] * sh1[j];
+        gate[(size_t)blockIdx.x * c + i] = 1.f / (1.f + __expf(-a));
+    }
+}
+}  // namespace
+
+extern "C" int fm_channel_gate4_pooled(const void* x0, const void* x1, const void* x2, const void* x3,
+                                       const float* gap_part, int strips, float* gate, const float* w1, const float* b1,
+                                       const float* w2, const float* b2, void* acc, int n, int hw, int c, int cr,
+                                       void* stream) {
+    if (n <= 0) return FM_OK;
+    if (c & 7) {
+        fm_set_last_error("fm_channel_gate4_pooled: channel count must be a multiple of 8");
+        return FM_ERR_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    Ptr4 p;
+    p.p[0] = (const __half*)x0; p.p[1] = (const __half*)x1; p.p[2] = (const __half*)x2; p.p[3] = (const __half*)x3;
+    gate_fc4_part_kernel<<<4 * n, 128, (c + cr) * sizeof(float), s>>>(gap_part, strips, n, hw, w1, b1, w2, b2, gate, c, cr);
+    const size_t total = (size_t)n * hw * c;
+    gate_apply4_vec<<<vgrid(total >> 3), 256, 0, s>>>(p, gate, (__half*)acc, (size_t)hw * c, n, c, total >> 3);
+    fm_count_launches(1);
+    FM_CHECK_LAUNCH("fm_channel_gate4_pooled");
+    return FM_OK;
+}
+
 extern "C" int fm_channel_gate4(const void* x0, const void* x1, const void* x2, const void* x3, float* pooled,
                                 float* gate, const float* w1, const float* b1, const float* w2, const float* b2,
                                 void* acc, int n, int hw, int c, int cr, void* stream) {

@@ -1,7 +1,7 @@
 // Fused OSNet OSBlock kernels for sm_100a (replace the per-layer launches of the ReID stack; role of the TensorRT
 // OSNet engine behind fastmot/utils/inference.py:106-117 + fastmot/feature_extractor.py:48-74).
 //
-// osb_streams_kernel<W, MID, T, NACC, NS>  ("kernel S")
+// osb_streams_kernel<W, MID, T, NACC, NS, NW>  ("kernel S")
 //   One CTA owns a strip of T x 128 pixels of one crop (all W columns, SR = 128 T / W rows) and computes, without
 //   leaving the SM,   x1 = relu(conv1x1(x) + b1)   and the four Lite-3x3 streams of the block
 //       stream s:  (1x1 linear conv -> depthwise 3x3 + bias + ReLU)  x (s + 1)
@@ -17,8 +17,8 @@
 //     zero row above and below.
 //   * strips of stage 1 carry a 4-row halo that is recomputed (4 = the deepest stream); rows outside the image are
 //     forced to zero after every pointwise conv (= the zero padding of the depthwise conv).
-//   Warp roles: 16 compute warps (TMEM lane quarter = warp & 3, channel quarter = warp >> 2), 1 control warp (one
-//   thread issues TMA, bulk copies and every tcgen05.mma).
+//   Warp roles: NW (8 or 16) compute warps (TMEM lane quarter = warp & 3, channel group = warp >> 2), 1 control warp
+//   (one thread issues TMA, bulk copies and every tcgen05.mma).
 //
 // Layouts: activations NHWC fp16; weight images are packed on the host (fastmot_b200/packing.py).
 #include "tc_common.cuh"
@@ -28,9 +28,6 @@ namespace {
 
 using namespace tc;
 
-constexpr int kComputeWarps = 16;
-constexpr int kComputeThreads = kComputeWarps * 32;
-constexpr int kThreadsS = kComputeThreads + 32;
 
 struct OsbStreamsArgs {
     int H, n_crops, cin, R, halo, strips;
@@ -57,6 +54,16 @@ __device__ __forceinline__ void tmem_ld_cols<24>(uint32_t taddr, uint32_t* r) {
 }
 template <>
 __device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t* r) { tmem_ld32(taddr, r); }
+template <>
+__device__ __forceinline__ void tmem_ld_cols<48>(uint32_t taddr, uint32_t* r) {
+    tmem_ld32(taddr, r);
+    tmem_ld16(taddr + 32, r + 32);
+}
+template <>
+__device__ __forceinline__ void tmem_ld_cols<64>(uint32_t taddr, uint32_t* r) {
+    tmem_ld32(taddr, r);
+    tmem_ld32(taddr + 32, r + 32);
+}
 
 // level -> (stream, depth in stream)
 __device__ __forceinline__ void level_sj(int lvl, int& s, int& j) {
@@ -66,12 +73,13 @@ __device__ __forceinline__ void level_sj(int lvl, int& s, int& j) {
     else { s = 3; j = lvl - 6; }
 }
 
-template <int W, int MID, int T, int NACC, int NS>
+template <int W, int MID, int T, int NACC, int NS, int NW>
 struct SCfg {
+    static constexpr int kThreads = NW * 32 + 32;
     static constexpr int SR = 128 * T / W;                  // strip rows
     static constexpr int RQ = 32 / W;                       // image rows per TMEM lane quarter and tile
     static constexpr int TROWS = 128 / W;                   // image rows per tile
-    static constexpr int CW = MID / 4;                      // channels per compute warp
+    static constexpr int CW = MID / (NW / 4);               // channels per compute warp
     static constexpr int NCH = MID / 8;                     // 16-byte chunks per pixel
     static constexpr int NSL = (MID + 63) / 64;             // K slices of the pointwise weights
     static constexpr int PW_BYTES = NSL * MID * 128;
@@ -84,23 +92,26 @@ struct SCfg {
     static constexpr int X1_COL = 0, ACT_COL = T * MID / 2, ACC_COL = T * MID;
     static constexpr int TMEM_NEED = ACC_COL + NACC * MID;
     static constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
-    static constexpr int SMEM = 1024 + PW_BYTES + 2 * ((DW_BYTES + 127) / 128 * 128) + REGION + 4 * 16 * CW;
+    static constexpr int DWB = (DW_BYTES + 127) / 128 * 128;  // one depthwise / bias blob
+    static constexpr int DW_AREA = (2 * DWB + 1023) / 1024 * 1024;   // keeps the swizzled region 1024-byte aligned
+    static constexpr int SMEM = 1024 + PW_BYTES + DW_AREA + REGION + 4 * NW * CW;
     static_assert(TMEM_NEED <= 512, "TMEM budget");
     static_assert(W == 8 || W == 16 || W == 32, "W");
     static_assert(MID % 32 == 0 && MID <= 128, "MID");
 };
 
-template <int W, int MID, int T, int NACC, int NS>
-__global__ void __launch_bounds__(kThreadsS, 1)
+template <int W, int MID, int T, int NACC, int NS, int NW>
+__global__ void __launch_bounds__(NW * 32 + 32, 1)
 osb_streams_kernel(const __grid_constant__ CUtensorMap map_x, OsbStreamsArgs a) {
-    using C = SCfg<W, MID, T, NACC, NS>;
+    using C = SCfg<W, MID, T, NACC, NS, NW>;
+    constexpr int kComputeWarps = NW, kComputeThreads = NW * 32;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* s_pw = smem;                                               // pointwise weight image (one level)
     uint8_t* s_dw0 = s_pw + C::PW_BYTES;                                // two depthwise / bias blobs
-    constexpr int DWB = (C::DW_BYTES + 127) / 128 * 128;
-    uint8_t* s_region = s_dw0 + 2 * DWB;                                // conv1 ring, later the P planes
-    float* s_gap = reinterpret_cast<float*>(s_region + C::REGION);      // [16 warps][CW]
+    constexpr int DWB = C::DWB;
+    uint8_t* s_region = s_dw0 + C::DW_AREA;                             // conv1 ring (1024-aligned), later the P planes
+    float* s_gap = reinterpret_cast<float*>(s_region + C::REGION);      // [NW warps][CW]
     __shared__ uint64_t ring_full[NS], ring_empty[NS], acc_full[NACC], acc_empty[NACC];
     __shared__ uint64_t pw_full, pw_empty, dw_full[2], act_ready;
     __shared__ uint32_t s_tmem;
@@ -382,9 +393,9 @@ osb_streams_kernel(const __grid_constant__ CUtensorMap map_x, OsbStreamsArgs a) 
     if (warp == kComputeWarps) tmem_dealloc<C::TMEM_COLS>(tmem);
 }
 
-template <int W, int MID, int T, int NACC, int NS>
+template <int W, int MID, int T, int NACC, int NS, int NW>
 int launch_streams(const FmOsbStreams* d, cudaStream_t st) {
-    using C = SCfg<W, MID, T, NACC, NS>;
+    using C = SCfg<W, MID, T, NACC, NS, NW>;
     OsbStreamsArgs a;
     a.H = d->h; a.n_crops = d->n; a.cin = d->cin;
     if (d->h == C::SR) { a.R = C::SR; a.halo = 0; a.strips = 1; }
@@ -399,11 +410,11 @@ int launch_streams(const FmOsbStreams* d, cudaStream_t st) {
     if (rc) return rc;
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(osb_streams_kernel<W, MID, T, NACC, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(osb_streams_kernel<W, MID, T, NACC, NS, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              C::SMEM);
         attr = true;
     }
-    cudaError_t e = fm_launch_pdl(osb_streams_kernel<W, MID, T, NACC, NS>, dim3(d->n * a.strips), dim3(kThreadsS),
+    cudaError_t e = fm_launch_pdl(osb_streams_kernel<W, MID, T, NACC, NS, NW>, dim3(d->n * a.strips), dim3(C::kThreads),
                                   (size_t)C::SMEM, st, map, a);
     if (e != cudaSuccess) { fm_set_last_error(cudaGetErrorString(e)); return FM_ERR_CUDA; }
     return FM_OK;
@@ -412,7 +423,7 @@ int launch_streams(const FmOsbStreams* d, cudaStream_t st) {
 }  // namespace
 
 extern "C" int fm_osb_streams_strips(int h, int w, int mid) {
-    if (w == 32 && mid == 64) return h % 8 == 0 && h >= 16 ? h / 8 : 0;
+    if (w == 32 && mid == 64) return h == 16 ? 1 : (h % 8 == 0 && h > 16 ? h / 8 : 0);   // 16 rows = one strip, no halo
     if (w == 16 && mid == 96) return h == 32 ? 1 : 0;
     if (w == 8 && mid == 128) return h == 16 ? 1 : 0;
     return 0;
@@ -425,9 +436,17 @@ extern "C" int fm_osb_streams(const FmOsbStreams* d, void* stream) {
     if (d->n <= 0) return FM_OK;
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    if (d->w == 32) rc = launch_streams<32, 64, 4, 4, 3>(d, st);
-    else if (d->w == 16) rc = launch_streams<16, 96, 4, 1, 3>(d, st);
-    else rc = launch_streams<8, 128, 1, 1, 2>(d, st);
+    static int nw = -1;            // FM_OSB_WARPS=8|16 compute warps per CTA (A/B timing)
+    if (nw < 0) { const char* e = getenv("FM_OSB_WARPS"); nw = (e && atoi(e) == 16) ? 16 : 8; }
+    if (nw == 16) {
+        if (d->w == 32) rc = launch_streams<32, 64, 4, 4, 3, 16>(d, st);
+        else if (d->w == 16) rc = launch_streams<16, 96, 4, 1, 3, 16>(d, st);
+        else rc = launch_streams<8, 128, 1, 1, 2, 16>(d, st);
+    } else {
+        if (d->w == 32) rc = launch_streams<32, 64, 4, 4, 3, 8>(d, st);
+        else if (d->w == 16) rc = launch_streams<16, 96, 4, 1, 3, 8>(d, st);
+        else rc = launch_streams<8, 128, 1, 1, 2, 8>(d, st);
+    }
     if (rc) return rc;
     FM_CHECK_LAUNCH("fm_osb_streams");
     return FM_OK;

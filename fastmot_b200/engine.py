@@ -33,8 +33,10 @@ class _Launch:
             _lib.check(rc, self.what)
 
 
-def _conv_desc(n, hi, wi, cin, cin_stride, cin_off, ho, wo, cout, cout_stride, cout_off, k, stride, pad, act):
+def _conv_desc(n, hi, wi, cin, cin_stride, cin_off, ho, wo, cout, cout_stride, cout_off, k, stride, pad, act, ws=None):
     d = _lib.FmConvDesc()
+    if ws is not None:       # fp32 split-K scratch (a torch uint8 tensor owned by the caller)
+        d.ws, d.ws_bytes = ws.data_ptr(), ws.numel()
     d.n, d.hi, d.wi, d.cin, d.cin_stride, d.cin_offset = n, hi, wi, cin, cin_stride, cin_off
     d.ho, d.wo, d.cout, d.cout_stride, d.cout_offset = ho, wo, cout, cout_stride, cout_off
     d.kh = d.kw = k
@@ -43,19 +45,9 @@ def _conv_desc(n, hi, wi, cin, cin_stride, cin_off, ho, wo, cout, cout_stride, c
     return d
 
 
-_WS = None
-
-
-def _ensure_workspace(lib, dev):
-    """fp32 split-K workspace of the tcgen05 conv (one per process; only the detector stream uses split-K)."""
-    global _WS
-    if _WS is None:
-        _WS = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
-        lib.fm_conv_set_workspace(C.c_void_p(_WS.data_ptr()), _WS.numel())
-
-
 class _Net:
     """Shared plumbing: recorded launches, optional CUDA-graph replay, conv dispatch (tcgen05 when supported)."""
+    WS_BYTES = 32 << 20
 
     def __init__(self, use_tc=True, use_graph=False):
         self._lib = _lib.require_device()
@@ -67,10 +59,12 @@ class _Net:
         self.n_tc = self.n_simt = 0
         self.layer_bytes = 0        # algorithmic HBM bytes of the conv / depthwise layers (each tensor moved once)
         self.dev = torch.device("cuda")
-        _ensure_workspace(self._lib, self.dev)
+        # split-K scratch of the tcgen05 conv: one per engine, so engines on different streams never share partials
+        self.ws = torch.empty(self.WS_BYTES, dtype=torch.uint8, device=self.dev)
 
     def _conv(self, desc, x, w, b, out, residual=None):
         lib = self._lib
+        desc.ws, desc.ws_bytes = self.ws.data_ptr(), self.ws.numel()
         self._keep.append(desc)
         self.layer_bytes += 2 * (desc.n * desc.hi * desc.wi * desc.cin + desc.n * desc.ho * desc.wo * desc.cout
                                  * (2 if residual is not None else 1) + desc.kh * desc.kw * desc.cin * desc.cout)
@@ -83,7 +77,8 @@ class _Net:
         self.launches.append(_Launch(fn, (C.byref(desc), ptr(x), ptr(w), ptr(b), ptr(residual), ptr(out)), "conv"))
 
     def kernels_per_replay(self):
-        return sum(3 if l.what == 'fm_channel_gate' else 1 for l in self.launches)
+        extra = {'fm_channel_gate': 2, 'fm_channel_gate4': 2, 'fm_channel_gate4_pooled': 1}
+        return sum(1 + extra.get(l.what, 0) for l in self.launches)
 
     def _add(self, fn_name, *args):
         self.launches.append(_Launch(getattr(self._lib, fn_name), args, fn_name))
@@ -277,12 +272,71 @@ class OSNetEngine(_Net):
         self.gate_tmp = torch.zeros(4 * B, 512, dtype=torch.float32, device=dev)
         self._params = params
         fused_add = {}
-        fused_dw = {}
+        # FM_OSB_FUSED=0 falls back to one launch per layer (r01 path); default: one fm_osb_streams launch per OSBlock
+        # for conv1 + the four Lite-3x3 streams (csrc/osnet_fused.cu)
+        self.fuse_osb = os.environ.get("FM_OSB_FUSED", "1") != "0" and use_tc
+        self.n_osb = 0
+        skip_until = -1
+        pooled_by_tail = {}
+        # FM_OSB_FUSED=0 falls back to one launch per layer (r01 path); default: one fm_osb_streams launch per OSBlock
+        # for conv1 + the four Lite-3x3 streams (csrc/osnet_fused.cu)
+        self.fuse_osb = os.environ.get("FM_OSB_FUSED", "1") != "0" and use_tc
+        self.n_osb = 0
+        skip_until = -1
+        pooled_by_tail = {}
         # FM_LITE_FUSED=1: run pointwise + depthwise of each Lite 3x3 as one kernel (experimental, default off)
         self.fuse_lite = os.environ.get("FM_LITE_FUSED", "0") == "1"
         self.n_lite = 0
         for k, op in enumerate(self.ops):
             kind = op[0]
+            if k <= skip_until:
+                continue
+            if kind == 'conv' and self.fuse_osb and op[1].endswith('.conv1'):
+                blk = self._match_osblock(k)
+                x, xc, h, w = live[op[8]]
+                if blk is not None and xc == op[2] and xc % 64 == 0 and \
+                        self._lib.fm_osb_streams_strips(h, w, op[3]) > 0:
+                    tails_names, gate_k = blk
+                    mid = op[3]
+                    strips = self._lib.fm_osb_streams_strips(h, w, mid)
+                    from .packing import pack_b_sw128
+                    w1, b1 = self.weights[op[1]]
+                    w1_img = torch.as_tensor(pack_b_sw128(w1.reshape(mid, xc))).to(dev)
+                    b1_d = torch.as_tensor(np.ascontiguousarray(b1, np.float32)).to(dev)
+                    pw_imgs, dw_blobs = [], []
+                    for i in range(10):
+                        pw_op, dw_op = self.ops[k + 1 + 2 * i], self.ops[k + 2 + 2 * i]
+                        wp, bp = self.weights[pw_op[1]]
+                        wd, bd = self.weights[dw_op[1]]
+                        pw_imgs.append(pack_b_sw128(wp.reshape(mid, mid)))
+                        dw_blobs.append(np.concatenate([np.ascontiguousarray(wd, np.float32).astype(np.float16)
+                                                        .reshape(-1).view(np.uint8),
+                                                        np.ascontiguousarray(bp, np.float32).view(np.uint8),
+                                                        np.ascontiguousarray(bd, np.float32).view(np.uint8)]))
+                    pw_d = torch.as_tensor(np.concatenate(pw_imgs)).to(dev)
+                    dw_d = torch.as_tensor(np.concatenate(dw_blobs)).to(dev)
+                    tails = [alloc(B * h * w * mid) for _ in range(4)]
+                    gap = torch.zeros(B * strips * 4 * mid, dtype=torch.float32, device=dev)
+                    d = _lib.FmOsbStreams()
+                    d.x, d.n, d.h, d.w, d.cin, d.mid = x.data_ptr(), B, h, w, xc, mid
+                    d.w1, d.b1, d.pw, d.dw = w1_img.data_ptr(), b1_d.data_ptr(), pw_d.data_ptr(), dw_d.data_ptr()
+                    for i in range(4):
+                        d.tails[i] = tails[i].data_ptr()
+                    d.gap_part = gap.data_ptr()
+                    self._keep += [d, w1_img, b1_d, pw_d, dw_d, gap]
+                    self._add('fm_osb_streams', C.byref(d))
+                    self.n_tc += 1
+                    self.n_osb += 1
+                    self.layer_bytes += 2 * (B * h * w * (xc + 4 * mid))
+                    for i, tn in enumerate(tails_names):
+                        live[tn] = (tails[i], mid, h, w)
+                    pooled_by_tail[tails_names[0]] = (gap, strips)
+                    # the block input may die here (no identity / downsample use): same bookkeeping as below
+                    for name in self._reads(op):
+                        if last.get(name) == k:
+                            release(name)
+                    skip_until = gate_k - 1
+                    continue
             if kind == 'conv':
                 _, name, cin, cout, ks, stride, pad, act, src, dst = op
                 x, xc, h, w = live[src]
@@ -295,22 +349,7 @@ class OSNetEngine(_Net):
                 params[name] = (wd, bd)
                 y = alloc(B * ho * wo * cout)
                 nxt = self.ops[k + 1] if k + 1 < len(self.ops) else None
-                if (self.fuse_lite and nxt is not None and nxt[0] == 'dw' and nxt[4] == dst and ks == 1
-                        and stride == 1 and pad == 0 and act == 'linear' and nxt[2] == cout
-                        and sum(dst in self._reads(o) for o in self.ops) == 1
-                        and self._lib.fm_lite3x3_supported(h, w, xc, cout)):
-                    # experimental: pointwise 1x1 + depthwise 3x3 of a Lite 3x3 block in one kernel
-                    wdw, bdw = dparam(nxt[1])
-                    wdw = wdw.half().contiguous()
-                    params[nxt[1]] = (wdw, bdw)
-                    self._add('fm_lite3x3', ptr(x), ptr(wd), ptr(bd), ptr(wdw), ptr(bdw), ptr(y), B, h, w, xc, cout,
-                              _ACT[nxt[3]])
-                    self.n_tc += 1
-                    self.n_lite += 1
-                    self.layer_bytes += 2 * (B * h * w * (xc + cout) + xc * cout + 9 * cout)
-                    fused_dw[k + 1] = True
-                    new = (nxt[5], (y, cout, h, w))
-                elif nxt is not None and nxt[0] == 'add_relu' and nxt[1] == dst and act == 'linear' and nxt[2] in live:
+                if nxt is not None and nxt[0] == 'add_relu' and nxt[1] == dst and act == 'linear' and nxt[2] in live:
                     # relu(conv3(x) + identity): residual + activation in the conv epilogue, no extra pass
                     d = _conv_desc(B, h, w, xc, xc, 0, ho, wo, cout, cout, 0, ks, stride, pad,
                                    _ACT['relu'] | ACT_AFTER_RESIDUAL)
@@ -323,8 +362,6 @@ class OSNetEngine(_Net):
                     self._conv(d, x, wd, bd, y)
                     new = (dst, (y, cout, ho, wo))
             elif kind == 'dw':
-                if k in fused_dw:         # folded into the preceding pointwise conv (fm_lite3x3)
-                    continue
                 _, name, c, act, src, dst = op
                 x, xc, h, w = live[src]
                 wd, bd = dparam(name)
@@ -361,8 +398,15 @@ class OSNetEngine(_Net):
                 _, xc, h, w = live[srcs[0]]
                 w1, b1, w2, b2 = dparam(name)
                 a = alloc(B * h * w * c)
-                self._add('fm_channel_gate4', ptr(xs[0]), ptr(xs[1]), ptr(xs[2]), ptr(xs[3]), ptr(self.pooled),
-                          ptr(self.gate_tmp), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(a), B, h * w, c, w1.shape[0])
+                if srcs[0] in pooled_by_tail:      # channel sums already produced by fm_osb_streams
+                    gap, strips = pooled_by_tail[srcs[0]]
+                    self._add('fm_channel_gate4_pooled', ptr(xs[0]), ptr(xs[1]), ptr(xs[2]), ptr(xs[3]), ptr(gap),
+                              strips, ptr(self.gate_tmp), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(a), B, h * w, c,
+                              w1.shape[0])
+                else:
+                    self._add('fm_channel_gate4', ptr(xs[0]), ptr(xs[1]), ptr(xs[2]), ptr(xs[3]), ptr(self.pooled),
+                              ptr(self.gate_tmp), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(a), B, h * w, c,
+                              w1.shape[0])
                 new = (acc, (a, c, h, w))
             elif kind == 'add_relu':
                 if k in fused_add:        # folded into the preceding conv's epilogue
@@ -392,6 +436,31 @@ class OSNetEngine(_Net):
                 if new[0] in live:
                     release(new[0])
                 live[new[0]] = new[1]
+
+    def _match_osblock(self, k):
+        """ops[k] = '<blk>.conv1'; returns (tail buffer names of the four streams, index of the gate4 op) when the next
+        twenty ops are the Lite-3x3 chains a.0, b.0, b.1, c.0 .. d.3 feeding that gate, else None."""
+        ops = self.ops
+        if k + 21 >= len(ops):
+            return None
+        x1 = ops[k][9]
+        mid = ops[k][3]
+        tails = []
+        i = k + 1
+        for s_ in range(4):
+            prev = x1
+            for j in range(s_ + 1):
+                pw, dw = ops[i], ops[i + 1]
+                if pw[0] != 'conv' or dw[0] != 'dw' or pw[2] != mid or pw[3] != mid or pw[4] != 1 or pw[7] != 'linear' \
+                        or pw[8] != prev or dw[4] != pw[9] or dw[2] != mid or dw[3] != 'relu':
+                    return None
+                prev = dw[5]
+                i += 2
+            tails.append(prev)
+        g = ops[i]
+        if g[0] != 'gate4' or tuple(g[3]) != tuple(tails) or ops[k][7] != 'relu':
+            return None
+        return tails, i
 
     @staticmethod
     def _reads(op):

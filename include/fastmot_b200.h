@@ -183,6 +183,11 @@ typedef struct FmConvDesc {
     int ho, wo, cout, cout_stride, cout_offset;     /* output [n][ho][wo][cout_stride], channels [off, off+cout) */
     int kh, kw, stride, pad, act;
     int res_stride, res_offset;                     /* optional residual added after the activation */
+    void* ws;                                       /* fp32 split-K scratch owned by the caller (one per engine /
+                                                       stream: convs that may run concurrently must not share it), or
+                                                       NULL = never split K.  Used when the 128 x BN output tiling
+                                                       alone cannot fill the 148 SMs (e.g. 20x20 layers at batch 1). */
+    long long ws_bytes;
 } FmConvDesc;
 
 /* weights: [cout][kh][kw][cin] fp16 (K-major), bias fp32[cout] or NULL, residual fp16 or NULL. */
@@ -192,11 +197,6 @@ int fm_conv2d_simt(const FmConvDesc* h_desc, const void* in, const void* wgt, co
 int fm_conv2d_tc(const FmConvDesc* h_desc, const void* in, const void* wgt, const float* bias, const void* residual,
                  void* out, void* stream);
 int fm_conv2d_tc_supported(const FmConvDesc* h_desc);
-/* fp32 scratch for split-K (used when the 128 x BN output tiling alone cannot fill the 148 SMs, e.g. 20x20 layers at
- * batch 1); NULL disables split-K.  The caller owns the memory; convs on different streams must not split concurrently.
- * The first 4 KB hold per-tile arrival counters and are zeroed by this call (a blocking cudaMemset: call it at set-up
- * time, not inside a stream capture); the partial sums follow. */
-int fm_conv_set_workspace(void* ws, long long bytes);
 /* Darknet maxpool (SAME_UPPER, yolo2onnx.py:838-863) with channel-slice in/out; PyTorch-style padded maxpool. */
 int fm_maxpool(const void* in, void* out, int n, int hi, int wi, int c, int cin_stride, int cin_off, int k, int stride,
                int cout_stride, int cout_off, void* stream);
@@ -205,13 +205,7 @@ int fm_avgpool2(const void* in, void* out, int n, int hi, int wi, int c, void* s
 /* nearest upsample (yolo2onnx.py:806-836) and/or route copy (:743-804): channel slice in -> channel slice out. */
 int fm_upsample_copy(const void* in, void* out, int n, int hi, int wi, int c, int cin_stride, int cin_off, int scale,
                      int cout_stride, int cout_off, void* stream);
-int fm_add_act(const void* a, const void* b, void* out, long long n, int act, void* stream); /* EXPERIMENTAL fused OSNet Lite 3x3 (torchreid LightConv3x3: 1x1 linear conv, then depthwise 3x3 + bias + act):
- * out[n][h][w][c] = act(dw3x3(in[n][h][w][cin] * w_pw[c][cin] + b_pw) + b_dw), NHWC fp16, zero padding applied to the
- * pointwise OUTPUT.  Same results as fm_conv2d_tc + fm_dwconv3 up to one fp16 rounding of the intermediate; the
- * engine uses it only with FM_LITE_FUSED=1.  cin % 8 == 0, 16 <= cin <= 128, c in {32, 64, 96, 128}, w % 4 == 0. */
-int fm_lite3x3(const void* in, const void* w_pw, const float* b_pw, const void* w_dw, const float* b_dw, void* out,
-               int n, int h, int w, int cin, int c, int act_dw, void* stream);
-int fm_lite3x3_supported(int h, int w, int cin, int c);
+int fm_add_act(const void* a, const void* b, void* out, long long n, int act, void* stream);
 /* shortcut :707-731 */
 int fm_add_act_strided(const void* a, int a_stride, int a_off, const void* b, int b_stride, int b_off, void* out,
                        int o_stride, int o_off, long long pixels, int c, int act, void* stream);
@@ -226,6 +220,10 @@ int fm_channel_gate(const void* x, float* pooled, float* gate, const float* w1, 
 int fm_channel_gate4(const void* x0, const void* x1, const void* x2, const void* x3, float* pooled, float* gate,
                      const float* w1, const float* b1, const float* w2, const float* b2, void* acc, int n, int hw, int c,
                      int cr, void* stream);
+/* Same aggregation with the pooling already done by fm_osb_streams: gap_part [n][strips][4][c] holds channel SUMS. */
+int fm_channel_gate4_pooled(const void* x0, const void* x1, const void* x2, const void* x3, const float* gap_part,
+                            int strips, float* gate, const float* w1, const float* b1, const float* w2, const float* b2,
+                            void* acc, int n, int hw, int c, int cr, void* stream);
 /* FC (+ReLU) and the row L2 normalisation of FeatureExtractor.postprocess (feature_extractor.py:73). */
 int fm_fc_norm(const float* in, const float* w, const float* bias, float* out, int n, int cin, int cout, int relu,
                int normalize, void* stream);

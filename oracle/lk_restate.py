@@ -159,6 +159,6 @@ def lk_track(prev, cur, pts, win=(5, 5), max_level=5, max_count=10, eps=0.03, mi
                             jv = (px(J, xx, yy) * v00 + px(J, xx + 1, yy) * v01 + px(J, xx, yy + 1) * v10 +
                                   px(J, xx + 1, yy + 1) * v11 + 256) >> 9
                             ev += abs(jv - Iv[y, x])
-                    err[pi] = f32(ev) * f32(1.0 / (32 * ww * wh))
+                    err[pi] = f32(ev) / f32(32 * ww * wh)
         out[pi] = (nx, ny)
     return out, status, err

@@ -4,9 +4,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from fastmot_b200 import _lib
 from fastmot_b200.devmem import ptr, stream_ptr
-from fastmot_b200.engine import _conv_desc, _ensure_workspace
+from fastmot_b200.engine import _conv_desc
 lib = _lib.require_device()
-_ensure_workspace(lib, torch.device("cuda"))
+WS = torch.empty(32 << 20, dtype=torch.uint8, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 DBG = "--dbg" in sys.argv
 dbg = torch.zeros(4096 * 8, dtype=torch.int64, device="cuda")
@@ -29,7 +29,7 @@ for (n, h, w, cin, cout, k, st) in SHAPES:
     wt = torch.randn(cout, k, k, cin, device="cuda").half()
     b = torch.zeros(cout, device="cuda")
     y = torch.zeros(n, ho, wo, cout, device="cuda").half()
-    d = _conv_desc(n, h, w, cin, cin, 0, ho, wo, cout, cout, 0, k, st, pad, 5)
+    d = _conv_desc(n, h, w, cin, cin, 0, ho, wo, cout, cout, 0, k, st, pad, 5, ws=WS)
     ts = []
     for it in range(6):
         flush.fill_(it)
