@@ -325,9 +325,9 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(FmConvDesc d, const __half
                                                        const __half* __restrict__ wgt, const float* __restrict__ bias,
                                                        const __half* __restrict__ residual, __half* __restrict__ out,
                                                        float* ws, int slices_per_split) {
-    extern __shared__ uint8_t smem_raw[];
-    // 1024-byte alignment for the 128B swizzle atoms
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment for the 128B swizzle atoms, by declaration (rounding the pointer through an integer makes the
+    // compiler fall back to generic LD / ST for the staged epilogue)
+    extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int A_BYTES = TC_BM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
     __shared__ uint64_t bar_stage[STAGES];
     __shared__ uint64_t bar_done;

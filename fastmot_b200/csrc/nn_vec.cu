@@ -589,21 +589,55 @@ __global__ void __launch_bounds__(128) gate_fc4_part_kernel(const float* __restr
 }
 }  // namespace
 
+namespace {
+// acc[b][p][c] = sum_s gate[s][b][c] * tail_s[b][c / 8][p][c % 8]: the tails come chunk-planar from fm_osb_streams (lanes
+// along the pixels on the read side), the sum leaves NHWC (lanes along the channels on the write side); 64 pixels per
+// block go through shared memory in between.
+__global__ void __launch_bounds__(256) gate_apply4_planar(Ptr4 x, const float* __restrict__ gate /* [4][n][c] */,
+                                                           __half* __restrict__ acc, int n, int hw, int c) {
+    extern __shared__ uint8_t sh_t[];
+    const int nch = c >> 3, pitch = c * 2 + 16;
+    const int blocks_per = hw >> 6;
+    const int b = blockIdx.x / blocks_per, p0 = (blockIdx.x - b * blocks_per) << 6;
+    for (int i = threadIdx.x; i < nch * 64; i += blockDim.x) {
+        const int chunk = i >> 6, px = i & 63;
+        float out[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) out[q] = 0.f;
+        const size_t off = (((size_t)b * nch + chunk) * hw + p0 + px) * 8;
+#pragma unroll
+        for (int st = 0; st < 4; ++st) {
+            float v[8];
+            to_f(ld8(x.p[st] + off), v);
+            const float* gp = gate + ((size_t)st * n + b) * c + chunk * 8;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) out[q] += v[q] * gp[q];
+        }
+        *reinterpret_cast<H8*>(sh_t + px * pitch + chunk * 16) = to_h(out);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nch * 64; i += blockDim.x) {
+        const int px = i / nch, chunk = i - px * nch;
+        st8(acc + ((size_t)b * hw + p0 + px) * c + chunk * 8, *reinterpret_cast<const H8*>(sh_t + px * pitch + chunk * 16));
+    }
+}
+}  // namespace
+
+// tails chunk-planar [n][c / 8][hw][8] (fm_osb_streams output), acc NHWC; hw must be a multiple of 64
 extern "C" int fm_channel_gate4_pooled(const void* x0, const void* x1, const void* x2, const void* x3,
                                        const float* gap_part, int strips, float* gate, const float* w1, const float* b1,
                                        const float* w2, const float* b2, void* acc, int n, int hw, int c, int cr,
                                        void* stream) {
     if (n <= 0) return FM_OK;
-    if (c & 7) {
-        fm_set_last_error("fm_channel_gate4_pooled: channel count must be a multiple of 8");
+    if ((c & 7) || (hw & 63)) {
+        fm_set_last_error("fm_channel_gate4_pooled: c must be a multiple of 8 and hw a multiple of 64");
         return FM_ERR_ARG;
     }
     cudaStream_t s = (cudaStream_t)stream;
     Ptr4 p;
     p.p[0] = (const __half*)x0; p.p[1] = (const __half*)x1; p.p[2] = (const __half*)x2; p.p[3] = (const __half*)x3;
     gate_fc4_part_kernel<<<4 * n, 128, (c + cr) * sizeof(float), s>>>(gap_part, strips, n, hw, w1, b1, w2, b2, gate, c, cr);
-    const size_t total = (size_t)n * hw * c;
-    gate_apply4_vec<<<vgrid(total >> 3), 256, 0, s>>>(p, gate, (__half*)acc, (size_t)hw * c, n, c, total >> 3);
+    gate_apply4_planar<<<n * (hw >> 6), 256, 64 * (c * 2 + 16), s>>>(p, gate, (__half*)acc, n, hw, c);
     fm_count_launches(1);
     FM_CHECK_LAUNCH("fm_channel_gate4_pooled");
     return FM_OK;

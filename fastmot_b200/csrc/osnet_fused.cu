@@ -29,13 +29,20 @@ namespace {
 using namespace tc;
 
 
+// optional phase stamps (scripts/osb_phases.py): clock64 of one CTA at the phase boundaries of every level
+__device__ long long* g_osb_dbg = nullptr;
+#define OSB_STAMP(slot)                                                                        \
+    do {                                                                                       \
+        if (g_osb_dbg && blockIdx.x == gridDim.x / 2) g_osb_dbg[(slot)] = clock64();           \
+    } while (0)
+
 struct OsbStreamsArgs {
     int H, n_crops, cin, R, halo, strips;
     const uint8_t* w1;      // conv1 weight image: cin/64 slices of [MID x 128 B]
     const float* b1;        // [MID]
     const uint8_t* pw;      // 10 pointwise images, each PW_BYTES
     const uint8_t* dw;      // 10 blobs, each DW_BYTES: [9][MID] fp16 | pw bias f32[MID] | dw bias f32[MID]
-    __half* tails[4];       // [n][H][W][MID] each
+    __half* tails[4];       // chunk-planar [n][MID / 8][H][W][8] each
     float* gap_part;        // [n][strips][4][MID]
 };
 
@@ -94,7 +101,7 @@ struct SCfg {
     static constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
     static constexpr int DWB = (DW_BYTES + 127) / 128 * 128;  // one depthwise / bias blob
     static constexpr int DW_AREA = (2 * DWB + 1023) / 1024 * 1024;   // keeps the swizzled region 1024-byte aligned
-    static constexpr int SMEM = 1024 + PW_BYTES + DW_AREA + REGION + 4 * NW * CW;
+    static constexpr int SMEM = PW_BYTES + DW_AREA + REGION + 4 * NW * CW;
     static_assert(TMEM_NEED <= 512, "TMEM budget");
     static_assert(W == 8 || W == 16 || W == 32, "W");
     static_assert(MID % 32 == 0 && MID <= 128, "MID");
@@ -105,8 +112,9 @@ __global__ void __launch_bounds__(NW * 32 + 32, 1)
 osb_streams_kernel(const __grid_constant__ CUtensorMap map_x, OsbStreamsArgs a) {
     using C = SCfg<W, MID, T, NACC, NS, NW>;
     constexpr int kComputeWarps = NW, kComputeThreads = NW * 32;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment comes from the declaration: rounding the pointer through an integer makes the compiler lose
+    // the shared address space and emit generic LD/ST (seen in SASS: ~3x slower depthwise loop)
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* s_pw = smem;                                               // pointwise weight image (one level)
     uint8_t* s_dw0 = s_pw + C::PW_BYTES;                                // two depthwise / bias blobs
     constexpr int DWB = C::DWB;
@@ -123,6 +131,7 @@ osb_streams_kernel(const __grid_constant__ CUtensorMap map_x, OsbStreamsArgs a) 
     const int nsl1 = a.cin >> 6;
 
     if (tid == 0) {
+        if (smem_u32(smem) & 1023u) __trap();                           // swizzled tiles need the alignment
         for (int i = 0; i < NS; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
         for (int i = 0; i < NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kComputeWarps); }
         mbar_init(&pw_full, 1); mbar_init(&pw_empty, 1);
@@ -139,6 +148,7 @@ osb_streams_kernel(const __grid_constant__ CUtensorMap map_x, OsbStreamsArgs a) 
     fence_after();
     const uint32_t tmem = s_tmem;
     fm_pdl_wait();
+    if (tid == 0) OSB_STAMP(0);
 
     if (warp == kComputeWarps) {
         // =========================================== control thread ===========================================
@@ -180,12 +190,19 @@ osb_streams_kernel(const __grid_constant__ CUtensorMap map_x, OsbStreamsArgs a) 
                 commit(&ring_empty[s]);
                 if (ks == nsl1 - 1) { commit(&acc_full[ai]); ++acc_use; }
             }
+            OSB_STAMP(1);
             // ---- the ten pointwise convs: A from TMEM ----
+            uint64_t bdesc_pw[MID / 16];
+#pragma unroll
+            for (int k = 0; k < MID / 16; ++k)
+                bdesc_pw[k] = smem_desc_sw128(smem_u32(s_pw) + (k >> 2) * MID * 128 + (k & 3) * 32);
             for (int lvl = 0; lvl < 10; ++lvl) {
                 int s, j;
                 level_sj(lvl, s, j);
                 mbar_wait(&pw_full, (uint32_t)(lvl & 1));
+                OSB_STAMP(16 + lvl * 16 + 0);
                 mbar_wait(&act_ready, (uint32_t)(lvl & 1));
+                OSB_STAMP(16 + lvl * 16 + 1);
                 fence_after();
                 const uint32_t a_base = tmem + (j == 0 ? C::X1_COL : C::ACT_COL);
                 for (int t = 0; t < T; ++t) {
@@ -194,19 +211,20 @@ osb_streams_kernel(const __grid_constant__ CUtensorMap map_x, OsbStreamsArgs a) 
                     fence_after();
 #pragma unroll
                     for (int k = 0; k < MID / 16; ++k)
-                        mma_ts(tmem + C::ACC_COL + ai * MID, a_base + t * (MID / 2) + k * 8,
-                               smem_desc_sw128(smem_u32(s_pw) + (k >> 2) * MID * 128 + (k & 3) * 32), idesc,
+                        mma_ts(tmem + C::ACC_COL + ai * MID, a_base + t * (MID / 2) + k * 8, bdesc_pw[k], idesc,
                                k > 0 ? 1u : 0u);
                     commit(&acc_full[ai]);
                     ++acc_use;
                 }
                 commit(&pw_empty);
+                OSB_STAMP(16 + lvl * 16 + 2);
                 if (lvl + 1 < 10) {
                     // the depthwise blob of level lvl - 1 is dead (act_ready of this level was its last reader)
                     uint8_t* sd = s_dw0 + ((lvl + 1) & 1) * DWB;
                     mbar_expect_tx(&dw_full[(lvl + 1) & 1], C::DW_BYTES);
                     bulk_load(sd, a.dw + (size_t)(lvl + 1) * C::DW_BYTES, C::DW_BYTES, &dw_full[(lvl + 1) & 1]);
                     mbar_wait(&pw_empty, (uint32_t)(lvl & 1));           // this level's MMAs have read s_pw
+                    OSB_STAMP(16 + lvl * 16 + 3);
                     mbar_expect_tx(&pw_full, C::PW_BYTES);
                     bulk_load(s_pw, a.pw + (size_t)(lvl + 1) * C::PW_BYTES, C::PW_BYTES, &pw_full);
                 }
@@ -227,7 +245,7 @@ osb_streams_kernel(const __grid_constant__ CUtensorMap map_x, OsbStreamsArgs a) 
             for (int i = 0; i < C::CW; ++i) b[i] = __ldg(a.b1 + c0 + i);
             for (int t = 0; t < T; ++t) {
                 const int ai = (int)(acc_use % NACC);
-                mbar_wait(&acc_full[ai], (uint32_t)((acc_use / NACC) & 1));
+                mbar_wait_sleep(&acc_full[ai], (uint32_t)((acc_use / NACC) & 1));
                 fence_after();
                 uint32_t r[C::CW];
                 tmem_ld_cols<C::CW>(lane_base + C::ACC_COL + ai * MID + c0, r);
@@ -266,36 +284,50 @@ osb_streams_kernel(const __grid_constant__ CUtensorMap map_x, OsbStreamsArgs a) 
             const __half* dww = reinterpret_cast<const __half*>(sd);                    // [9][MID]
             const float* bpw = reinterpret_cast<const float*>(sd + 9 * MID * 2);        // [MID]
             const float* bdw = bpw + MID;                                               // [MID]
-            mbar_wait(&dw_full[lvl & 1], (uint32_t)((lvl >> 1) & 1));
-            // pointwise epilogue: acc + bias -> fp16 (zero outside the image) -> P planes
-            for (int t = 0; t < T; ++t) {
-                const int ai = (int)(acc_use % NACC);
-                mbar_wait(&acc_full[ai], (uint32_t)((acc_use / NACC) & 1));
-                fence_after();
-                uint32_t r[C::CW];
-                tmem_ld_cols<C::CW>(lane_base + C::ACC_COL + ai * MID + c0, r);
-                tmem_ld_wait();
-                fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[ai]);
-                ++acc_use;
-                const int yloc = run * T + t, y = y0 + yloc;
-                const bool inside = y >= 0 && y < a.H;
+            __half* tail_base = s == 0 ? a.tails[0] : s == 1 ? a.tails[1] : s == 2 ? a.tails[2] : a.tails[3];
+            mbar_wait_sleep(&dw_full[lvl & 1], (uint32_t)((lvl >> 1) & 1));
+            // pointwise epilogue: acc + bias -> fp16 (zero outside the image) -> P planes.  The TMEM load of tile
+            // t + 1 is issued before tile t is converted (two register buffers).
+            {
+                uint32_t rbuf[2][C::CW];
+                auto fetch = [&](int t, uint32_t* r) {
+                    const int ai = (int)((acc_use + t) % NACC);
+                    mbar_wait_sleep(&acc_full[ai], (uint32_t)(((acc_use + t) / NACC) & 1));
+                    fence_after();
+                    tmem_ld_cols<C::CW>(lane_base + C::ACC_COL + ai * MID + c0, r);
+                };
+                if (tid == 0) OSB_STAMP(16 + lvl * 16 + 4);
+                fetch(0, rbuf[0]);
+                if (tid == 0) OSB_STAMP(16 + lvl * 16 + 5);
 #pragma unroll
-                for (int i = 0; i < C::CW / 8; ++i) {
-                    uint32_t p[4];
+                for (int t = 0; t < T; ++t) {
+                    uint32_t* r = rbuf[t & 1];
+                    tmem_ld_wait();
+                    fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[(int)((acc_use + t) % NACC)]);
+                    if (t + 1 < T && NACC > 1) fetch(t + 1, rbuf[(t + 1) & 1]);
+                    const int yloc = run * T + t, y = y0 + yloc;
+                    const bool inside = y >= 0 && y < a.H;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int ch = c0 + i * 8 + 2 * e;
-                        p[e] = inside ? pack_h2(__uint_as_float(r[i * 8 + 2 * e]) + bpw[ch],
-                                                __uint_as_float(r[i * 8 + 2 * e + 1]) + bpw[ch + 1])
-                                      : 0u;
+                    for (int i = 0; i < C::CW / 8; ++i) {
+                        const float4 ba = *reinterpret_cast<const float4*>(bpw + c0 + i * 8);
+                        const float4 bb = *reinterpret_cast<const float4*>(bpw + c0 + i * 8 + 4);
+                        uint32_t p[4];
+                        p[0] = pack_h2(__uint_as_float(r[i * 8 + 0]) + ba.x, __uint_as_float(r[i * 8 + 1]) + ba.y);
+                        p[1] = pack_h2(__uint_as_float(r[i * 8 + 2]) + ba.z, __uint_as_float(r[i * 8 + 3]) + ba.w);
+                        p[2] = pack_h2(__uint_as_float(r[i * 8 + 4]) + bb.x, __uint_as_float(r[i * 8 + 5]) + bb.y);
+                        p[3] = pack_h2(__uint_as_float(r[i * 8 + 6]) + bb.z, __uint_as_float(r[i * 8 + 7]) + bb.w);
+                        *reinterpret_cast<uint4*>(s_region + (size_t)(c0 / 8 + i) * C::PLANE + ((yloc + 1) * W + x) * 16) =
+                            inside ? make_uint4(p[0], p[1], p[2], p[3]) : make_uint4(0u, 0u, 0u, 0u);
                     }
-                    *reinterpret_cast<uint4*>(s_region + (size_t)(c0 / 8 + i) * C::PLANE +
-                                              ((yloc + 1) * W + x) * 16) = make_uint4(p[0], p[1], p[2], p[3]);
+                    if (t + 1 < T && NACC == 1) fetch(t + 1, rbuf[(t + 1) & 1]);
                 }
+                acc_use += T;
             }
+            if (tid == 0) OSB_STAMP(16 + lvl * 16 + 6);
             named_bar_sync(1, kComputeThreads);
+            if (tid == 0) OSB_STAMP(16 + lvl * 16 + 7);
             // depthwise 3x3 + bias + ReLU over the vertical run of this thread
             float gsum[8];
 #pragma unroll
@@ -316,7 +348,7 @@ osb_streams_kernel(const __grid_constant__ CUtensorMap map_x, OsbStreamsArgs a) 
 #pragma unroll
                     for (int e = 0; e < 8; ++e) gsum[e] = 0.f;
                 }
-                uint4 win[3][3];
+                uint4 win[4][3];
                 auto load_row = [&](int r, uint4 (&dst)[3]) {
                     const uint8_t* rp = plane + (size_t)r * W * 16;
                     dst[1] = *reinterpret_cast<const uint4*>(rp + x * 16);
@@ -325,15 +357,16 @@ osb_streams_kernel(const __grid_constant__ CUtensorMap map_x, OsbStreamsArgs a) 
                 };
                 load_row(0, win[0]);
                 load_row(1, win[1]);
+                load_row(2, win[2]);
 #pragma unroll
                 for (int t = 0; t < T; ++t) {
-                    load_row(t + 2, win[(t + 2) % 3]);
+                    if (t + 1 < T) load_row(t + 3, win[(t + 3) & 3]);      // next output's new row, before the math
                     __half2 o[4] = {bias2[0], bias2[1], bias2[2], bias2[3]};
 #pragma unroll
                     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
                         for (int dx = 0; dx < 3; ++dx) {
-                            const uint4& v = win[(t + dy) % 3][dx];
+                            const uint4& v = win[(t + dy) & 3][dx];
                             o[0] = __hfma2(wv[dy * 3 + dx][0], *reinterpret_cast<const __half2*>(&v.x), o[0]);
                             o[1] = __hfma2(wv[dy * 3 + dx][1], *reinterpret_cast<const __half2*>(&v.y), o[1]);
                             o[2] = __hfma2(wv[dy * 3 + dx][2], *reinterpret_cast<const __half2*>(&v.z), o[2]);
@@ -351,7 +384,8 @@ osb_streams_kernel(const __grid_constant__ CUtensorMap map_x, OsbStreamsArgs a) 
                     } else {
                         const int yloc = run * T + t, y = y0 + yloc;
                         if (yloc >= a.halo && yloc < a.halo + a.R && y < a.H) {
-                            *reinterpret_cast<uint4*>(a.tails[s] + (((size_t)crop * a.H + y) * W + x) * MID + c8 * 8) =
+                            // chunk-planar tail [crop][chunk][y][x][8]: a warp writes whole 16-byte-per-pixel rows
+                            *reinterpret_cast<uint4*>(tail_base + ((((size_t)crop * C::NCH + c8) * a.H + y) * W + x) * 8) =
                                 make_uint4(p[0], p[1], p[2], p[3]);
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
@@ -383,6 +417,7 @@ osb_streams_kernel(const __grid_constant__ CUtensorMap map_x, OsbStreamsArgs a) 
             } else {
                 tmem_st_wait();
             }
+            if (tid == 0) OSB_STAMP(16 + lvl * 16 + 8);
             fence_before();
             __syncwarp();
             if (lane == 0 && lvl + 1 < 10) mbar_arrive(&act_ready);
@@ -422,6 +457,12 @@ int launch_streams(const FmOsbStreams* d, cudaStream_t st) {
 
 }  // namespace
 
+extern "C" int fm_osb_set_debug(void* dbg) {     // debugging aid, not part of the public header
+    long long* p = (long long*)dbg;
+    cudaMemcpyToSymbol(g_osb_dbg, &p, sizeof(p));
+    return FM_OK;
+}
+
 extern "C" int fm_osb_streams_strips(int h, int w, int mid) {
     if (w == 32 && mid == 64) return h == 16 ? 1 : (h % 8 == 0 && h > 16 ? h / 8 : 0);   // 16 rows = one strip, no halo
     if (w == 16 && mid == 96) return h == 32 ? 1 : 0;
@@ -436,17 +477,9 @@ extern "C" int fm_osb_streams(const FmOsbStreams* d, void* stream) {
     if (d->n <= 0) return FM_OK;
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    static int nw = -1;            // FM_OSB_WARPS=8|16 compute warps per CTA (A/B timing)
-    if (nw < 0) { const char* e = getenv("FM_OSB_WARPS"); nw = (e && atoi(e) == 16) ? 16 : 8; }
-    if (nw == 16) {
-        if (d->w == 32) rc = launch_streams<32, 64, 4, 4, 3, 16>(d, st);
-        else if (d->w == 16) rc = launch_streams<16, 96, 4, 1, 3, 16>(d, st);
-        else rc = launch_streams<8, 128, 1, 1, 2, 16>(d, st);
-    } else {
-        if (d->w == 32) rc = launch_streams<32, 64, 4, 4, 3, 8>(d, st);
-        else if (d->w == 16) rc = launch_streams<16, 96, 4, 1, 3, 8>(d, st);
-        else rc = launch_streams<8, 128, 1, 1, 2, 8>(d, st);
-    }
+    if (d->w == 32) rc = launch_streams<32, 64, 4, 4, 3, 8>(d, st);
+    else if (d->w == 16) rc = launch_streams<16, 96, 4, 1, 3, 8>(d, st);
+    else rc = launch_streams<8, 128, 1, 1, 2, 8>(d, st);
     if (rc) return rc;
     FM_CHECK_LAUNCH("fm_osb_streams");
     return FM_OK;

@@ -45,8 +45,7 @@ namespace {
 __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUtensorMap map_a, int row0,
                                                      const uint8_t* __restrict__ b1, const uint8_t* __restrict__ b2,
                                                      int n1, int n2, float* __restrict__ out0, float* __restrict__ out1) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;                       // 128 x 128 B
     uint8_t* sB1 = sA + 16384;                // n1 x 128 B
     uint8_t* sB2 = sB1 + 128 * 128;           // ceil(n1 / 64) slices of n2 x 128 B

@@ -220,7 +220,8 @@ int fm_channel_gate(const void* x, float* pooled, float* gate, const float* w1, 
 int fm_channel_gate4(const void* x0, const void* x1, const void* x2, const void* x3, float* pooled, float* gate,
                      const float* w1, const float* b1, const float* w2, const float* b2, void* acc, int n, int hw, int c,
                      int cr, void* stream);
-/* Same aggregation with the pooling already done by fm_osb_streams: gap_part [n][strips][4][c] holds channel SUMS. */
+/* Same aggregation fed by fm_osb_streams: x0..x3 are its chunk-planar tails [n][c / 8][hw][8], gap_part
+ * [n][strips][4][c] holds their channel SUMS; acc is NHWC.  hw % 64 == 0. */
 int fm_channel_gate4_pooled(const void* x0, const void* x1, const void* x2, const void* x3, const float* gap_part,
                             int strips, float* gate, const float* w1, const float* b1, const float* w2, const float* b2,
                             void* acc, int n, int hw, int c, int cr, void* stream);
@@ -316,7 +317,7 @@ int fm_probe_umma(const void* a, int rows, int row0, const void* b1, const void*
 /* ---------------------------------------------------------------- fused OSNet OSBlock kernels --------------- */
 /* Kernel S (csrc/osnet_fused.cu): conv1 (1x1, cin -> mid, ReLU) and the four Lite-3x3 streams of one OSBlock
  * (torchreid OSBlock.conv1 / conv2a..d; role of the TensorRT OSNet engine, fastmot/utils/inference.py:106-117) in a
- * single launch.  x: [n][h][w][cin] fp16 NHWC; tails[s]: [n][h][w][mid] fp16 (output of stream s);
+ * single launch.  x: [n][h][w][cin] fp16 NHWC; tails[s]: chunk-planar [n][mid / 8][h][w][8] fp16 (output of stream s);
  * gap_part: fp32 [n][strips][4][mid], the per-strip channel sums of the tails (strips = fm_osb_streams_strips()).
  * w1: fm pack_b_sw128 image of the conv1 weights [mid][cin]; pw: ten pack_b_sw128 images [mid][mid] in the order
  * a.0, b.0, b.1, c.0, c.1, c.2, d.0 .. d.3; dw: ten blobs { fp16 [9][mid] depthwise taps, fp32 [mid] pointwise bias,

@@ -55,7 +55,7 @@ def run_osb_streams(x, w1, b1, pws, dws):
         blobs.append(np.concatenate([wd.astype(np.float16).reshape(-1).view(np.uint8),
                                      bp.astype(np.float32).view(np.uint8), bd.astype(np.float32).view(np.uint8)]))
     dw_d = torch.as_tensor(np.concatenate(blobs)).to(dev)
-    tails = [torch.full((n, h, w, mid), float('nan'), dtype=torch.float16, device=dev) for _ in range(4)]
+    tails = [torch.full((n, mid // 8, h, w, 8), float('nan'), dtype=torch.float16, device=dev) for _ in range(4)]
     gap = torch.full((n, strips, 4, mid), float('nan'), dtype=torch.float32, device=dev)
     d = _lib.FmOsbStreams()
     d.x, d.n, d.h, d.w, d.cin, d.mid = x.data_ptr(), n, h, w, cin, mid
@@ -65,6 +65,8 @@ def run_osb_streams(x, w1, b1, pws, dws):
     d.gap_part = gap.data_ptr()
     _lib.check(lib.fm_osb_streams(C.byref(d), stream_ptr()), "fm_osb_streams")
     torch.cuda.synchronize()
+    # chunk-planar [n][mid / 8][h][w][8] -> NHWC
+    tails = [t.permute(0, 2, 3, 1, 4).reshape(n, h, w, mid) for t in tails]
     return tails, gap.sum(1)
 
 
