@@ -44,6 +44,12 @@ class FmOsbStreams(C.Structure):
                 ("pw", c_p), ("dw", c_p), ("tails", c_p * 4), ("gap_part", c_p)]
 
 
+class FmOsbMerge(C.Structure):
+    _fields_ = [("n", c_i), ("hw", c_i), ("cin", c_i), ("cout", c_i), ("mid", c_i), ("cr", c_i), ("strips", c_i),
+                ("tails", c_p * 4), ("gap_part", c_p), ("gw1", c_p), ("gb1", c_p), ("gw2", c_p), ("gb2", c_p),
+                ("wimg", c_p), ("bias", c_p), ("x", c_p), ("res", c_p), ("out", c_p)]
+
+
 class FmYoloHead(C.Structure):
     _fields_ = [("anchors", c_f * 12), ("scale_x_y", c_f)]
 
@@ -102,6 +108,8 @@ SIGNATURES = {
     "fm_probe_umma": (c_i, [c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p]),
     "fm_osb_streams": (c_i, [C.POINTER(FmOsbStreams), c_p]),
     "fm_osb_streams_strips": (c_i, [c_i, c_i, c_i]),
+    "fm_osb_merge": (c_i, [C.POINTER(FmOsbMerge), c_p]),
+    "fm_osb_merge_ncta": (c_i, [c_i, c_i]),
     "fm_channel_gate4_pooled": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i,
                                       c_p]),
     "fm_nms_mask_bytes": (c_ll, [c_i]),

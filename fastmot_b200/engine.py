@@ -392,6 +392,57 @@ class OSNetEngine(_Net):
                 self._add('fm_channel_gate', ptr(x), ptr(self.pooled), ptr(self.gate_tmp), ptr(w1), ptr(b1), ptr(w2),
                           ptr(b2), ptr(a), B, h * w, c, w1.shape[0], accumulate)
                 new = None
+            elif kind == 'gate4' and op[3][0] in pooled_by_tail and self._match_merge(k) is not None and \
+                    self._lib.fm_osb_merge_ncta(op[2], self._match_merge(k)[1][3]) > 0:
+                # gate + conv3 (+ downsample) + residual + ReLU in one launch (kernel G)
+                _, name, c, srcs, acc = op
+                ds_op, c3_op, add_op, last_k = self._match_merge(k)
+                from .packing import pack_b_sw128
+                xs = [live[s_][0] for s_ in srcs]
+                _, _, h, w = live[srcs[0]]
+                gap, strips = pooled_by_tail[srcs[0]]
+                gw1, gb1, gw2, gb2 = dparam(name)
+                cout = c3_op[3]
+                ncta = self._lib.fm_osb_merge_ncta(c, cout)
+                w3, b3 = self.weights[c3_op[1]]
+                wcat = w3.reshape(cout, c)
+                bias = np.asarray(b3, np.float32).copy()
+                ident_name = add_op[2] if add_op[1] == c3_op[9] else add_op[1]
+                d = _lib.FmOsbMerge()
+                if ds_op is not None:
+                    wdn, bdn = self.weights[ds_op[1]]
+                    cin = ds_op[2]
+                    wcat = np.concatenate([wdn.reshape(cout, cin), wcat], 1)
+                    bias += np.asarray(bdn, np.float32)
+                    xin = live[ds_op[8]]
+                    d.x, d.res, d.cin = xin[0].data_ptr(), None, cin
+                else:
+                    d.x, d.res, d.cin = None, live[ident_name][0].data_ptr(), cout
+                img = np.concatenate([pack_b_sw128(wcat[r:r + ncta]) for r in range(0, cout, ncta)])
+                img_d = torch.as_tensor(img).to(dev)
+                bias_d = torch.as_tensor(bias).to(dev)
+                y = alloc(B * h * w * cout)
+                d.n, d.hw, d.cout, d.mid, d.cr, d.strips = B, h * w, cout, c, gw1.shape[0], strips
+                for i in range(4):
+                    d.tails[i] = xs[i].data_ptr()
+                d.gap_part = gap.data_ptr()
+                d.gw1, d.gb1, d.gw2, d.gb2 = (t_.data_ptr() for t_ in (gw1, gb1, gw2, gb2))
+                d.wimg, d.bias, d.out = img_d.data_ptr(), bias_d.data_ptr(), y.data_ptr()
+                self._keep += [d, img_d, bias_d]
+                self._add('fm_osb_merge', C.byref(d))
+                self.n_tc += 1
+                self.n_merge = getattr(self, 'n_merge', 0) + 1
+                self.layer_bytes += 2 * (B * h * w * (4 * c + 2 * cout))
+                # bookkeeping of the skipped ops' reads
+                for kk in range(k, last_k + 1):
+                    for nm in self._reads(self.ops[kk]):
+                        if last.get(nm) == kk:
+                            release(nm)
+                if add_op[3] in live:
+                    release(add_op[3])
+                live[add_op[3]] = (y, cout, h, w)
+                skip_until = last_k
+                continue
             elif kind == 'gate4':
                 _, name, c, srcs, acc = op
                 xs = [live[s_][0] for s_ in srcs]
@@ -461,6 +512,28 @@ class OSNetEngine(_Net):
         if g[0] != 'gate4' or tuple(g[3]) != tuple(tails) or ops[k][7] != 'relu':
             return None
         return tails, i
+
+    def _match_merge(self, k):
+        """ops[k] = gate4 of an OSBlock; returns (downsample conv or None, conv3, add_relu, index of add_relu) when
+        the ops that follow are [downsample 1x1] conv3 1x1 (linear, reads the gate output) and add_relu."""
+        ops = self.ops
+        acc = ops[k][4]
+        i = k + 1
+        ds = None
+        if i < len(ops) and ops[i][0] == 'conv' and ops[i][1].endswith('.downsample'):
+            ds = ops[i]
+            i += 1
+        if i + 1 >= len(ops):
+            return None
+        c3, add = ops[i], ops[i + 1]
+        if c3[0] != 'conv' or c3[4] != 1 or c3[7] != 'linear' or c3[8] != acc or add[0] != 'add_relu':
+            return None
+        if c3[9] not in (add[1], add[2]):
+            return None
+        other = add[2] if add[1] == c3[9] else add[1]
+        if ds is not None and (ds[4] != 1 or ds[7] != 'linear' or ds[9] != other or ds[2] % 64):
+            return None
+        return ds, c3, add, i + 1
 
     @staticmethod
     def _reads(op):

@@ -336,6 +336,27 @@ int fm_osb_streams(const FmOsbStreams* h_desc, void* stream);
 /* number of strips per crop kernel S uses for this geometry (0 = unsupported) */
 int fm_osb_streams_strips(int h, int w, int mid);
 
+/* Kernel G: the rest of the OSBlock in one launch (torchreid OSBlock: gate, conv3, downsample, residual, ReLU):
+ *   out = relu(conv3(sum_s gate(tail_s) * tail_s) + b3 + identity),  identity = res (cin == cout) or downsample(x).
+ * tails / gap_part: outputs of fm_osb_streams; gw1 [cr][mid], gb1 [cr], gw2 [mid][cr], gb2 [mid]: gate FCs (fp32);
+ * wimg: for every range of fm_osb_merge_ncta(mid, cout) output channels, the pack_b_sw128 image of the rows of
+ * [W_down | W_3] (K = cin, then mid rounded up to 64; W_down only when x != NULL); bias [cout] = b3 (+ b_down);
+ * exactly one of x ([n][hw][cin], downsample input) and res ([n][hw][cout], identity) is non-NULL; out [n][hw][cout].
+ * hw % 128 == 0, cr <= 8. */
+typedef struct FmOsbMerge {
+    int n, hw, cin, cout, mid, cr, strips;
+    const void* tails[4];
+    const float* gap_part;
+    const float* gw1; const float* gb1; const float* gw2; const float* gb2;
+    const void* wimg;
+    const float* bias;
+    const void* x;
+    const void* res;
+    void* out;
+} FmOsbMerge;
+int fm_osb_merge(const FmOsbMerge* h_desc, void* stream);
+int fm_osb_merge_ncta(int mid, int cout);
+
 #ifdef __cplusplus
 }
 #endif

@@ -146,3 +146,81 @@ def test_osnet_x1_fused_engine_vs_oracle_and_unfused(batch, graph, monkeypatch):
     want = nets.run_osnet(eng.ops, eng.weights, inp[:nb, ..., :3].float().permute(0, 3, 1, 2), nets.fp16_roundtrip)
     np.testing.assert_allclose(got.norm(dim=1).numpy(), 1.0, atol=1e-4)
     assert float((got[:nb] - want).abs().max()) < 5e-3, float((got[:nb] - want).abs().max())
+
+
+def run_osb_merge(tails, gw, w3, b3, wd=None, bd=None, x=None, res=None):
+    """tails: 4 x (n, h, w, mid) fp16 cuda (NHWC); returns out (n, h*w, cout) fp16."""
+    from fastmot_b200 import _lib
+    from fastmot_b200.devmem import stream_ptr
+    from fastmot_b200.packing import pack_b_sw128
+    lib = _lib.require_device()
+    n, h, w, mid = tails[0].shape
+    cout = w3.shape[0]
+    ncta = lib.fm_osb_merge_ncta(mid, cout)
+    assert ncta > 0
+    dev = tails[0].device
+    planar = [t.reshape(n, h, w, mid // 8, 8).permute(0, 3, 1, 2, 4).contiguous() for t in tails]
+    strips = 2       # split the channel sums over two "strips" to exercise the strip reduction
+    gap = torch.zeros(n, strips, 4, mid, dtype=torch.float32, device=dev)
+    for s in range(4):
+        tf = tails[s].float()
+        gap[:, 0, s] = tf[:, :h // 2].sum((1, 2))
+        gap[:, 1, s] = tf[:, h // 2:].sum((1, 2))
+    wcat, bias = w3, b3.copy()
+    if wd is not None:
+        wcat = np.concatenate([wd, w3], 1)
+        bias = bias + bd
+    img = torch.as_tensor(np.concatenate([pack_b_sw128(wcat[r:r + ncta]) for r in range(0, cout, ncta)])).to(dev)
+    bias_d = torch.as_tensor(bias.astype(np.float32)).to(dev)
+    gws = [torch.as_tensor(np.ascontiguousarray(a, np.float32)).to(dev) for a in gw]
+    out = torch.full((n, h * w, cout), float('nan'), dtype=torch.float16, device=dev)
+    d = _lib.FmOsbMerge()
+    d.n, d.hw, d.cout, d.mid, d.cr, d.strips = n, h * w, cout, mid, gw[0].shape[0], strips
+    d.cin = wd.shape[1] if wd is not None else cout
+    for i in range(4):
+        d.tails[i] = planar[i].data_ptr()
+    d.gap_part = gap.data_ptr()
+    d.gw1, d.gb1, d.gw2, d.gb2 = (g.data_ptr() for g in gws)
+    d.wimg, d.bias, d.out = img.data_ptr(), bias_d.data_ptr(), out.data_ptr()
+    d.x = x.data_ptr() if x is not None else None
+    d.res = res.data_ptr() if res is not None else None
+    _lib.check(lib.fm_osb_merge(C.byref(d), stream_ptr()), "fm_osb_merge")
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("w,mid,h,cin,cout,n", [(32, 64, 64, 64, 256, 2), (32, 64, 64, 256, 256, 2),
+                                                (16, 96, 32, 256, 384, 3), (16, 96, 32, 384, 384, 2),
+                                                (8, 128, 16, 384, 512, 5), (8, 128, 16, 512, 512, 3)])
+def test_osb_merge_vs_torch(w, mid, h, cin, cout, n):
+    rng = np.random.default_rng(cin + cout)
+    g = torch.Generator().manual_seed(cin)
+    tails = [(torch.randn(n, h, w, mid, generator=g).abs() * 0.6).half() for _ in range(4)]
+    cr = mid // 16
+    gw = (rng.normal(0, np.sqrt(2.0 / mid), (cr, mid)), rng.normal(0, 0.1, cr),
+          rng.normal(0, np.sqrt(2.0 / cr), (mid, cr)), rng.normal(0, 0.1, mid))
+    w3 = rng.normal(0, np.sqrt(1.0 / mid), (cout, mid)).astype(np.float32)
+    b3 = rng.normal(0, 0.05, cout).astype(np.float32)
+    down = cin != cout
+    if down:
+        wd = rng.normal(0, np.sqrt(1.0 / cin), (cout, cin)).astype(np.float32)
+        bd = rng.normal(0, 0.05, cout).astype(np.float32)
+        x = (torch.randn(n, h * w, cin, generator=g).abs() * 0.7).half()
+        got = run_osb_merge([t.cuda() for t in tails], gw, w3, b3, wd, bd, x=x.cuda())
+    else:
+        res = (torch.randn(n, h * w, cout, generator=g).abs() * 0.7).half()
+        got = run_osb_merge([t.cuda() for t in tails], gw, w3, b3, res=res.cuda())
+    t = lambda a: torch.as_tensor(np.asarray(a, np.float32))
+    u = 0
+    for s in range(4):
+        tf = tails[s].float()
+        gate = torch.sigmoid(F.relu(tf.mean((1, 2)) @ t(gw[0]).T + t(gw[1])) @ t(gw[2]).T + t(gw[3]))
+        u = u + tf * gate[:, None, None, :]
+    u = _h(u).reshape(n, h * w, mid)
+    y = u @ _h(t(w3)).T + t(b3)
+    y = y + (x.float() @ _h(t(wd)).T + t(bd) if down else res.float())
+    want = _h(F.relu(y))
+    gotc = got.float().cpu()
+    assert torch.isfinite(gotc).all()
+    err = float((gotc - want).abs().max()) / (float(want.abs().max()) + 1e-6)
+    assert err < 4e-3, err
