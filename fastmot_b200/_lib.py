@@ -47,7 +47,7 @@ class FmOsbStreams(C.Structure):
 class FmOsbMerge(C.Structure):
     _fields_ = [("n", c_i), ("hw", c_i), ("cin", c_i), ("cout", c_i), ("mid", c_i), ("cr", c_i), ("strips", c_i),
                 ("tails", c_p * 4), ("gap_part", c_p), ("gw1", c_p), ("gb1", c_p), ("gw2", c_p), ("gb2", c_p),
-                ("wimg", c_p), ("bias", c_p), ("x", c_p), ("res", c_p), ("out", c_p)]
+                ("wimg", c_p), ("bias", c_p), ("x", c_p), ("res", c_p), ("out", c_p), ("gate_scratch", c_p)]
 
 
 class FmYoloHead(C.Structure):
@@ -110,6 +110,7 @@ SIGNATURES = {
     "fm_osb_streams_strips": (c_i, [c_i, c_i, c_i]),
     "fm_osb_merge": (c_i, [C.POINTER(FmOsbMerge), c_p]),
     "fm_osb_merge_ncta": (c_i, [c_i, c_i]),
+    "fm_osnet_stem": (c_i, [c_p, c_i, c_p, c_p, c_p, c_p]),
     "fm_channel_gate4_pooled": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i,
                                       c_p]),
     "fm_nms_mask_bytes": (c_ll, [c_i]),

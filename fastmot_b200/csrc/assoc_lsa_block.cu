@@ -140,11 +140,152 @@ __global__ void __launch_bounds__(1024) lsa_block_kernel(const double* __restric
 #undef COST
 }
 
+
+// -----------------------------------------------------------------------------------------------------------------
+// Version 2 (columns <= 1024): one column per thread with all per-column state in registers (reduced cost spc,
+// dual v, path, row4col, position in SciPy's `remaining` array), ONE barrier per inner step and no serial section:
+// every warp publishes its (minimum, last unassigned tie, first tie) and all threads reduce the <= 32 entries
+// redundantly.  The cost row of the next `curRow` is prefetched while the current row is solved, the visited rows'
+// dual updates use u[r] += minVal - (minVal at the step that reached r) -- the same value SciPy reads back as
+// shortestPathCosts[col4row[r]] -- and only the augmenting-path walk (a few links) is done by one thread.
+// Same replay of scipy/optimize/rectangular_lsap/rectangular_lsap.cpp as above: scan order of `remaining`
+// (positions), swap-with-last compaction, "last unassigned among equal minima, else first minimum", fp64 operation
+// order -> bit-exact assignments, also with ties.
+// -----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long dkey(double d) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+struct WarpEntry { unsigned long long key; int posU, posF, colU, colF, r4cF, pad; };
+
+__global__ void __launch_bounds__(1024) lsa_v2_kernel(const double* __restrict__ cost, int nr0, int nc0,
+                                                       int* __restrict__ out_col4row, int* __restrict__ status) {
+    __shared__ double s_u[1024], s_vmv[1024];
+    __shared__ int s_col4row[1024], s_path[1024], s_r4c[1024], s_vrow[1024];
+    __shared__ WarpEntry s_ent[2][32];
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarps = T >> 5;
+    const bool transpose = nc0 < nr0;
+    const int nr = transpose ? nc0 : nr0;
+    const int nc = transpose ? nr0 : nc0;
+    const int j = tid;
+    const bool mine = j < nc;
+    const size_t sj = transpose ? (size_t)j * nc0 : (size_t)j, si = transpose ? (size_t)1 : (size_t)nc0;
+#define COST2(i) (cost[sj + (size_t)(i) * si])
+    for (int k = tid; k < nr; k += T) { s_u[k] = 0.0; s_col4row[k] = -1; }
+    double v = 0.0;
+    int r4c = -1, path = -1;
+    double nxt = mine ? COST2(0) : 0.0;
+    const unsigned long long KINF = dkey(INFINITY);
+    bool infeasible = false;
+    __syncthreads();
+    for (int cur = 0; cur < nr; ++cur) {
+        double spc = INFINITY;
+        int pos = mine ? nc - 1 - j : -1;
+        bool sc = false;
+        int num = nc, i = cur, sink = -1, nvis = 0, par = 0;
+        double minVal = 0.0;
+        double c_i = nxt;
+        if (mine && cur + 1 < nr) nxt = COST2(cur + 1);
+        while (true) {
+            if (tid == 0) { s_vrow[nvis] = i; s_vmv[nvis] = minVal; }
+            ++nvis;
+            const double ui = s_u[i];
+            unsigned long long key = KINF;
+            if (pos >= 0) {
+                const double r = __dsub_rn(__dsub_rn(__dadd_rn(minVal, c_i), ui), v);
+                if (r < spc) { spc = r; path = i; }
+                key = dkey(spc + 0.0);          // -0.0 and +0.0 compare equal in SciPy's '<'; give them one key
+            }
+            // warp minimum of the 64-bit order-preserving keys
+            const unsigned hi = (unsigned)(key >> 32);
+            const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+            const unsigned lo = hi == mhi ? (unsigned)key : 0xffffffffu;
+            const unsigned mlo = __reduce_min_sync(0xffffffffu, lo);
+            const unsigned long long wkey = ((unsigned long long)mhi << 32) | mlo;
+            const bool tie = pos >= 0 && key == wkey;
+            const int posU = __reduce_max_sync(0xffffffffu, (tie && r4c == -1) ? pos : -1);
+            const int posF = __reduce_min_sync(0xffffffffu, tie ? pos : 0x7fffffff);
+            WarpEntry& e = s_ent[par][wid];
+            if (lane == 0) { e.key = wkey; e.posU = posU; e.posF = posF; }
+            if (tie && pos == posU) e.colU = j;
+            if (tie && pos == posF) { e.colF = j; e.r4cF = r4c; }
+            __syncthreads();
+            unsigned long long gkey = KINF;
+            for (int w = 0; w < nwarps; ++w) gkey = min(gkey, s_ent[par][w].key);
+            if (gkey == KINF) { infeasible = true; break; }
+            int bestU = -1, colU = -1, bestF = 0x7fffffff, colF = -1, r4cF = -1;
+            for (int w = 0; w < nwarps; ++w) {
+                const WarpEntry& q = s_ent[par][w];
+                if (q.key != gkey) continue;
+                if (q.posU > bestU) { bestU = q.posU; colU = q.colU; }
+                if (q.posF < bestF) { bestF = q.posF; colF = q.colF; r4cF = q.r4cF; }
+            }
+            const int idx = bestU >= 0 ? bestU : bestF;
+            const int jsel = bestU >= 0 ? colU : colF;
+            const int rsel = bestU >= 0 ? -1 : r4cF;
+            // minVal = the winning spc (decode the key back to the double)
+            minVal = __longlong_as_double((long long)((gkey >> 63) ? (gkey & 0x7fffffffffffffffull) : ~gkey));
+            if (j == jsel) { sc = true; pos = -1; }
+            else if (pos == num - 1) pos = idx;
+            --num;
+            if (rsel == -1) { sink = jsel; break; }
+            i = rsel;
+            if (pos >= 0) c_i = COST2(i);
+            par ^= 1;
+        }
+        if (infeasible) break;
+        // dual updates (SciPy: u[cur] += minVal; u[r] += minVal - spc[col4row[r]] for visited r; v[j] -= minVal - spc[j])
+        if (tid == 0) s_u[cur] = __dadd_rn(s_u[cur], minVal);
+        if (tid >= 1 && tid < nvis) {
+            const int r = s_vrow[tid];
+            s_u[r] = __dadd_rn(s_u[r], __dsub_rn(minVal, s_vmv[tid]));
+        }
+        if (sc) v = __dsub_rn(v, __dsub_rn(minVal, spc));
+        if (mine) { s_path[j] = path; s_r4c[j] = r4c; }
+        __syncthreads();
+        if (tid == 0) {
+            int jj = sink;
+            while (true) {
+                const int ii = s_path[jj];
+                s_r4c[jj] = ii;
+                const int tmp = s_col4row[ii];
+                s_col4row[ii] = jj;
+                jj = tmp;
+                if (ii == cur) break;
+            }
+        }
+        __syncthreads();
+        if (mine) r4c = s_r4c[j];
+    }
+    if (infeasible) {
+        if (tid == 0) status[0] = 1;
+        for (int k = tid; k < nr0; k += T) out_col4row[k] = -1;
+        return;
+    }
+    if (tid == 0) status[0] = 0;
+    __syncthreads();
+    for (int k = tid; k < nr0; k += T) {
+        int c = transpose ? s_r4c[k] : s_col4row[k];
+        if (c >= 0 && cost[(size_t)k * nc0 + c] >= FM_INF_COST) c = -2 - c;
+        out_col4row[k] = c;
+    }
+#undef COST2
+}
+
 }  // namespace
 
 int fm_launch_lsa_block(const double* cost, int nr, int nc, int* col4row, int* status, unsigned char* ws, int use_smem,
                         size_t smem_bytes, cudaStream_t s) {
     const int big = nr > nc ? nr : nc;
+    static int v1 = -1;            // FM_LSA_V1=1: previous CTA-wide kernel (A/B timing)
+    if (v1 < 0) { const char* e = getenv("FM_LSA_V1"); v1 = (e && e[0] == '1') ? 1 : 0; }
+    if (big <= 1024 && !v1) {
+        int t2 = 64;
+        while (t2 < big) t2 <<= 1;
+        lsa_v2_kernel<<<1, t2, 0, s>>>(cost, nr, nc, col4row, status);
+        return 0;
+    }
     int threads = 64;
     while (threads < big && threads < 1024) threads <<= 1;
     lsa_block_kernel<<<1, threads, use_smem ? smem_bytes : 0, s>>>(cost, nr, nc, col4row, status, ws, use_smem);

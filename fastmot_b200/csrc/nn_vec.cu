@@ -623,6 +623,14 @@ __global__ void __launch_bounds__(256) gate_apply4_planar(Ptr4 x, const float* _
 }
 }  // namespace
 
+// gate FCs of one OSBlock from the strip sums (shared with fm_osb_merge): gate[4][n][c]
+int fm_gate_fc4_part(const float* gap_part, int strips, int n, int hw, const float* w1, const float* b1, const float* w2,
+                     const float* b2, float* gate, int c, int cr, cudaStream_t s) {
+    gate_fc4_part_kernel<<<4 * n, 128, (c + cr) * sizeof(float), s>>>(gap_part, strips, n, hw, w1, b1, w2, b2, gate, c, cr);
+    fm_count_launches(1);
+    return FM_OK;
+}
+
 // tails chunk-planar [n][c / 8][hw][8] (fm_osb_streams output), acc NHWC; hw must be a multiple of 64
 extern "C" int fm_channel_gate4_pooled(const void* x0, const void* x1, const void* x2, const void* x3,
                                        const float* gap_part, int strips, float* gate, const float* w1, const float* b1,

@@ -128,8 +128,8 @@ struct SCfg {
 // Cluster barrier protocol (every thread of the cluster alternates arrive / wait):
 //   arrive (conv1 ring dead)  |  per level:  wait -> pointwise epilogue (local + remote rows) -> arrive, wait ->
 //   depthwise -> arrive  |  final wait.
-template <int W, int MID, int T, int NACC, int NS, int NW, int CL>
-__global__ void __launch_bounds__(NW * 32 + 32, 1)
+template <int W, int MID, int T, int NACC, int NS, int NW, int CL, int MINB>
+__global__ void __launch_bounds__(NW * 32 + 32, MINB)
 osb_streams_kernel(const __grid_constant__ CUtensorMap map_x, OsbStreamsArgs a) {
     using C = SCfg<W, MID, T, NACC, NS, NW, CL>;
     constexpr int kComputeWarps = NW, kComputeThreads = NW * 32;
@@ -486,7 +486,7 @@ osb_streams_kernel(const __grid_constant__ CUtensorMap map_x, OsbStreamsArgs a) 
     if (warp == kComputeWarps) tmem_dealloc<C::TMEM_COLS>(tmem);
 }
 
-template <int W, int MID, int T, int NACC, int NS, int NW, int CL>
+template <int W, int MID, int T, int NACC, int NS, int NW, int CL, int MINB = 1>
 int launch_streams(const FmOsbStreams* d, cudaStream_t st) {
     using C = SCfg<W, MID, T, NACC, NS, NW, CL>;
     OsbStreamsArgs a;
@@ -504,7 +504,7 @@ int launch_streams(const FmOsbStreams* d, cudaStream_t st) {
     if (rc) return rc;
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(osb_streams_kernel<W, MID, T, NACC, NS, NW, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(osb_streams_kernel<W, MID, T, NACC, NS, NW, CL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              C::SMEM);
         attr = true;
     }
@@ -527,7 +527,7 @@ int launch_streams(const FmOsbStreams* d, cudaStream_t st) {
     }
     cfg.attrs = attrs;
     cfg.numAttrs = na;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, osb_streams_kernel<W, MID, T, NACC, NS, NW, CL>, map, a);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, osb_streams_kernel<W, MID, T, NACC, NS, NW, CL, MINB>, map, a);
     if (e != cudaSuccess) { fm_set_last_error(cudaGetErrorString(e)); return FM_ERR_CUDA; }
     return FM_OK;
 }
@@ -543,11 +543,16 @@ int launch_streams(const FmOsbStreams* d, cudaStream_t st) {
 // [W_down | W_3] stream through the same ring by cp.async.bulk.  Epilogue: TMEM -> fp16 staging tile -> coalesced
 // rows (+ identity rows read coalesced) -> ReLU -> NHWC.
 // =====================================================================================================================
+}  // namespace
+int fm_gate_fc4_part(const float* gap_part, int strips, int n, int hw, const float* w1, const float* b1, const float* w2,
+                     const float* b2, float* gate, int c, int cr, cudaStream_t s);    // nn_vec.cu
+namespace {
+
 struct OsbMergeArgs {
     int n, hw, cin, cout, strips, has_down, cr;
     const __half* tails[4];      // chunk-planar [n][MID / 8][hw][8]
     const float* gap_part;       // [n][strips][4][MID]
-    const float* gw1; const float* gb1; const float* gw2; const float* gb2;   // gate FCs: [cr][MID], [cr], [MID][cr], [MID]
+    const float* gates;          // [4][n][MID] sigmoid gates (gate_fc4_part_kernel)
     const uint8_t* wimg;         // per N range: (cin / 64 if has_down) + NSLU slices of [NCTA x 128 B]
     const float* bias;           // [cout] = b3 (+ b_down)
     const __half* res;           // identity [n][hw][cout] or NULL
@@ -564,7 +569,7 @@ struct GCfg {
     static constexpr int PITCH = NCTA * 2 + 16;             // staging row
     static constexpr int STG = 128 * PITCH;
     static constexpr int REGION = RING > STG ? RING : STG;
-    static constexpr int SMEM = REGION + 4 * MID * 4 + 4 * 8 * 4 + 4 * MID * 4;
+    static constexpr int SMEM = REGION + 4 * MID * 4;
     static_assert(NSLU <= NS, "the u slices live in distinct ring stages");
     static constexpr int TMEM_COLS = NCTA <= 128 ? 128 : 256;
     static constexpr int kThreads = 8 * 32 + 32;
@@ -577,9 +582,7 @@ osb_merge_kernel(const __grid_constant__ CUtensorMap map_x, OsbMergeArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* s_region = smem;                                    // ring (A slice | weight slice), later the staging tile
     float* s_gate = reinterpret_cast<float*>(smem + C::REGION);  // [4][MID]
-    float* s_hid = s_gate + 4 * MID;                             // [4][8]
-    float* s_pool = s_hid + 32;                                  // [4][MID]
-    __shared__ uint64_t ring_full[C::NS], ring_empty[C::NS], u_ready, acc_full;
+    __shared__ uint64_t ring_full[C::NS], ring_empty[C::NS], u_ready, acc_full, u_free[C::NSLU];
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     fm_pdl_trigger();
@@ -593,6 +596,7 @@ osb_merge_kernel(const __grid_constant__ CUtensorMap map_x, OsbMergeArgs a) {
         for (int i = 0; i < C::NS; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
         mbar_init(&u_ready, 8);
         mbar_init(&acc_full, 1);
+        for (int i = 0; i < C::NSLU; ++i) mbar_init(&u_free[i], 1);
         mbar_fence_init();
     }
     if (warp == 8) {
@@ -616,6 +620,9 @@ osb_merge_kernel(const __grid_constant__ CUtensorMap map_x, OsbMergeArgs a) {
             uint8_t* sa = s_region + (size_t)st * C::STAGE;
             if (leader) {
                 const bool isx = i < nslx;
+                // the stage's A half now belongs to the compute warps (they build slice i - nslx of u in place).  A
+                // single-use barrier: a warp that is not in lock step with the ring cannot use its parity waits.
+                if (!isx) mbar_arrive(&u_free[i - nslx]);
                 mbar_expect_tx(&ring_full[st], (isx ? 16384u : 0u) + (uint32_t)C::BSL);
                 if (isx) tma_load_3d(sa, &map_x, &ring_full[st], i * 64, p0, crop);
                 bulk_load(sa + 16384, wimg + (size_t)i * C::BSL, C::BSL, &ring_full[st]);
@@ -642,35 +649,16 @@ osb_merge_kernel(const __grid_constant__ CUtensorMap map_x, OsbMergeArgs a) {
     } else {
         // ------------------------------------------- compute warps -------------------------------------------
         constexpr int NCH = MID / 8;
-        // gates of this crop
+        // gates of this crop (computed once per crop by the small FC kernel launched before this one)
         for (int i = tid; i < 4 * MID; i += 256) {
             const int st = i / MID, c = i - st * MID;
-            float v = 0.f;
-            for (int k = 0; k < a.strips; ++k) v += a.gap_part[(((size_t)crop * a.strips + k) * 4 + st) * MID + c];
-            s_pool[i] = v / (float)a.hw;
-        }
-        named_bar_sync(1, 256);
-        if (tid < 4 * a.cr) {
-            const int st = tid / a.cr, j = tid - st * a.cr;
-            float v = a.gb1[j];
-            for (int c = 0; c < MID; ++c) v += a.gw1[j * MID + c] * s_pool[st * MID + c];
-            s_hid[st * 8 + j] = fmaxf(v, 0.f);
-        }
-        named_bar_sync(1, 256);
-        for (int i = tid; i < 4 * MID; i += 256) {
-            const int st = i / MID, c = i - st * MID;
-            float v = a.gb2[c];
-            for (int j = 0; j < a.cr; ++j) v += a.gw2[c * a.cr + j] * s_hid[st * 8 + j];
-            s_gate[i] = 1.f / (1.f + __expf(-v));
+            s_gate[i] = a.gates[((size_t)st * a.n + crop) * MID + c];
         }
         named_bar_sync(1, 256);
         // u tile: item = (chunk, pixel); lanes run along the pixels (coalesced planar reads, conflict-free swizzled
         // writes).  Slice k of u is the A operand of ring iteration nslx + k and is written straight into that stage.
 #pragma unroll
-        for (int k = 0; k < C::NSLU; ++k) {
-            const int it = nslx + k;
-            if (it >= C::NS) mbar_wait_sleep(&ring_empty[it % C::NS], (uint32_t)((it / C::NS - 1) & 1));
-        }
+        for (int k = 0; k < C::NSLU; ++k) mbar_wait_sleep(&u_free[k], 0);
         for (int i = tid; i < NCH * 128; i += 256) {
             const int c8 = i >> 7, px = i & 127;
             const size_t off = (((size_t)crop * NCH + c8) * a.hw + p0 + px) * 8;
@@ -761,7 +749,7 @@ int launch_merge(const FmOsbMerge* d, cudaStream_t st) {
     a.has_down = d->x != nullptr;
     for (int i = 0; i < 4; ++i) a.tails[i] = (const __half*)d->tails[i];
     a.gap_part = d->gap_part;
-    a.gw1 = d->gw1; a.gb1 = d->gb1; a.gw2 = d->gw2; a.gb2 = d->gb2;
+    a.gates = d->gate_scratch;
     a.wimg = (const uint8_t*)d->wimg; a.bias = d->bias; a.res = (const __half*)d->res; a.out = (__half*)d->out;
     CUtensorMap map;
     memset(&map, 0, sizeof map);
@@ -796,9 +784,12 @@ extern "C" int fm_osb_merge(const FmOsbMerge* d, void* stream) {
     FM_REQUIRE(d->hw % 128 == 0 && d->cr >= 1 && d->cr <= 8 && d->strips >= 1, "fm_osb_merge: hw / cr / strips");
     FM_REQUIRE((d->x != nullptr) != (d->res != nullptr), "fm_osb_merge: exactly one of x (downsample) and res (identity)");
     FM_REQUIRE(d->x == nullptr || (d->cin % 64 == 0 && d->cin >= 64), "fm_osb_merge: cin must be a multiple of 64");
+    FM_REQUIRE(d->gate_scratch != nullptr, "fm_osb_merge: gate_scratch (4 * n * mid floats) is NULL");
     if (d->n <= 0) return FM_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    int rc;
+    int rc = fm_gate_fc4_part(d->gap_part, d->strips, d->n, d->hw, d->gw1, d->gb1, d->gw2, d->gb2, d->gate_scratch, d->mid,
+                              d->cr, st);
+    if (rc) return rc;
     if (d->mid == 64) rc = launch_merge<64, 256>(d, st);
     else if (d->mid == 96) rc = launch_merge<96, 192>(d, st);
     else rc = launch_merge<128, 256>(d, st);
@@ -822,7 +813,10 @@ extern "C" int fm_osb_streams_strips(int h, int w, int mid) {
         if (!(e && e[0] == '0')) return 4;          // one 4-CTA cluster per crop
     }
     if (w == 32 && mid == 64) return h == 16 ? 1 : (h % 8 == 0 && h > 16 ? h / 8 : 0);   // 16 rows = one strip, no halo
-    if (w == 16 && mid == 96) return h == 32 ? 1 : 0;
+    if (w == 16 && mid == 96 && h == 32) {
+        const char* e = getenv("FM_OSB_CLUSTER");
+        return (e && e[0] == '0') ? 1 : 2;          // two-CTA cluster per crop
+    }
     if (w == 8 && mid == 128) return h == 16 ? 1 : 0;
     return 0;
 }
@@ -838,10 +832,14 @@ extern "C" int fm_osb_streams(const FmOsbStreams* d, void* stream) {
     if (nw < 0) { const char* e = getenv("FM_OSB_WARPS"); nw = (e && atoi(e) == 16) ? 16 : 8; }
     static int cl = -1;            // FM_OSB_CLUSTER=0: strips with a recomputed 4-row halo instead of the 4-CTA cluster
     if (cl < 0) { const char* e = getenv("FM_OSB_CLUSTER"); cl = (e && e[0] == '0') ? 0 : 1; }
-    if (d->w == 32 && d->h == 64 && cl) rc = launch_streams<32, 64, 4, 4, 3, 8, 4>(d, st);
-    else if (d->w == 32 && nw == 16) rc = launch_streams<32, 64, 4, 4, 3, 16, 1>(d, st);
+    static int s3b = -1;           // FM_OSB_S3_BLOCKS=1: one stage-3 CTA per SM (default two)
+    if (s3b < 0) { const char* e = getenv("FM_OSB_S3_BLOCKS"); s3b = (e && e[0] == '1') ? 1 : 2; }
+    if (d->w == 32 && d->h == 64 && cl && nw == 16) rc = launch_streams<32, 64, 4, 4, 3, 16, 4>(d, st);
+    else if (d->w == 32 && d->h == 64 && cl) rc = launch_streams<32, 64, 4, 4, 3, 8, 4>(d, st);
     else if (d->w == 32) rc = launch_streams<32, 64, 4, 4, 3, 8, 1>(d, st);
+    else if (d->w == 16 && cl) rc = launch_streams<16, 96, 2, 2, 3, 8, 2>(d, st);       // two 16-row strips per crop
     else if (d->w == 16) rc = launch_streams<16, 96, 4, 1, 3, 8, 1>(d, st);
+    else if (s3b == 2) rc = launch_streams<8, 128, 1, 1, 2, 8, 1, 2>(d, st);
     else rc = launch_streams<8, 128, 1, 1, 2, 8, 1>(d, st);
     if (rc) return rc;
     FM_CHECK_LAUNCH("fm_osb_streams");

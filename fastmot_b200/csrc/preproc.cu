@@ -11,9 +11,16 @@
 
 namespace {
 
-template <int LAYOUT>  // 0: fp32 CHW, 1: fp16 NHWC8
+template <int LAYOUT>  // 0: fp32 CHW, 1: fp16 NHWC8, 2: fp16 NHWC4 inside a 4-pixel zero border ([H + 8][W + 8][4])
 __device__ __forceinline__ void store_px(void* out, int H, int W, int y, int x, float r, float g, float b) {
-    if (LAYOUT == 0) {
+    if (LAYOUT == 2) {
+        // 8 bytes per pixel; the border (never written here, zeroed once by the owner of the buffer) is the zero
+        // padding of the 7x7 stem, so its TMA tiles need no bounds handling (csrc/osnet_stem.cu)
+        __align__(8) __half2 v[2];
+        v[0] = __floats2half2_rn(r, g);
+        v[1] = __floats2half2_rn(b, 0.0f);
+        *reinterpret_cast<int2*>((__half*)out + ((size_t)(y + 4) * (W + 8) + x + 4) * 4) = *reinterpret_cast<const int2*>(v);
+    } else if (LAYOUT == 0) {
         float* o = (float*)out;
         size_t plane = (size_t)H * W, p = (size_t)y * W + x;
         o[p] = r; o[plane + p] = g; o[2 * plane + p] = b;
@@ -111,7 +118,8 @@ __global__ void __launch_bounds__(128) roi_resize_norm_kernel(const unsigned cha
         v[c] = (float)(((double)px / 255.0 - (double)mean[c]) / (double)stdv[c]);
     }
     void* o = LAYOUT == 0 ? (void*)((float*)out + (size_t)crop * 3 * out_h * out_w)
-                          : (void*)((__half*)out + (size_t)crop * 8 * out_h * out_w);
+              : LAYOUT == 1 ? (void*)((__half*)out + (size_t)crop * 8 * out_h * out_w)
+                            : (void*)((__half*)out + (size_t)crop * 4 * (out_h + 8) * (out_w + 8));
     store_px<LAYOUT>(o, out_h, out_w, y, x, v[2], v[1], v[0]);
 }
 
@@ -135,15 +143,18 @@ extern "C" int fm_letterbox_preproc(const unsigned char* frame, int src_w, int s
 extern "C" int fm_roi_resize_norm(const unsigned char* frame, int src_w, int src_h, const double* tlbrs,
                                   const int* n_dev, int n_max, int out_w, int out_h, int layout, void* out,
                                   void* stream) {
-    FM_REQUIRE(layout == 0 || layout == 1, "fm_roi_resize_norm: layout must be 0 (f32 CHW) or 1 (f16 NHWC8)");
+    FM_REQUIRE(layout >= 0 && layout <= 2, "fm_roi_resize_norm: layout must be 0 (f32 CHW), 1 (f16 NHWC8) or 2 (f16 NHWC4, padded)");
     if (n_max <= 0) return FM_OK;
     FM_REQUIRE(n_max <= 65535, "fm_roi_resize_norm: more than 65535 crops");
     dim3 grid(fm_cdiv(out_w, 128), out_h, n_max);
     if (layout == 0)
         roi_resize_norm_kernel<0><<<grid, 128, 0, (cudaStream_t)stream>>>(frame, src_w, src_h, tlbrs, n_dev, n_max,
                                                                           out_w, out_h, out);
-    else
+    else if (layout == 1)
         roi_resize_norm_kernel<1><<<grid, 128, 0, (cudaStream_t)stream>>>(frame, src_w, src_h, tlbrs, n_dev, n_max,
+                                                                          out_w, out_h, out);
+    else
+        roi_resize_norm_kernel<2><<<grid, 128, 0, (cudaStream_t)stream>>>(frame, src_w, src_h, tlbrs, n_dev, n_max,
                                                                           out_w, out_h, out);
     FM_CHECK_LAUNCH("fm_roi_resize_norm");
     return FM_OK;

@@ -77,11 +77,17 @@ class _Net:
         self.launches.append(_Launch(fn, (C.byref(desc), ptr(x), ptr(w), ptr(b), ptr(residual), ptr(out)), "conv"))
 
     def kernels_per_replay(self):
-        extra = {'fm_channel_gate': 2, 'fm_channel_gate4': 2, 'fm_channel_gate4_pooled': 1}
+        extra = {'fm_channel_gate': 2, 'fm_channel_gate4': 2, 'fm_channel_gate4_pooled': 1, 'fm_osb_merge': 1}
         return sum(1 + extra.get(l.what, 0) for l in self.launches)
 
     def _add(self, fn_name, *args):
         self.launches.append(_Launch(getattr(self._lib, fn_name), args, fn_name))
+
+    def warm(self, n=3):
+        """Replays the recorded network n times (graph capture included) so the first timed call is steady state."""
+        for _ in range(n):
+            self.replay()
+        torch.cuda.synchronize()
 
     def replay(self):
         _lib.count_graph_kernels(self.kernels_per_replay() if self.use_graph and self._graph is not None else 0)
@@ -236,7 +242,19 @@ class OSNetEngine(_Net):
         self.macs_per_crop = osnet.count_macs(self.ops, *input_hw)
         B, (H, W) = max_batch, input_hw
         dev = self.dev
-        self.inp = torch.zeros(B, H, W, IN_C_PAD, dtype=torch.float16, device=dev)
+        # FM_OSB_FUSED=0 falls back to one launch per layer (r01 path); default: fused stem (fm_osnet_stem), one
+        # fm_osb_streams + fm_osb_merge pair per OSBlock (csrc/osnet_fused.cu, csrc/osnet_stem.cu)
+        self.fuse_osb = os.environ.get("FM_OSB_FUSED", "1") != "0" and use_tc
+        first, second = self.ops[0], self.ops[1]
+        self.fuse_stem = (self.fuse_osb and os.environ.get("FM_OSB_STEM", "1") != "0" and (H, W) == (256, 128)
+                          and first[0] == 'conv' and first[2:8] == (3, 64, 7, 2, 3, 'relu') and second[0] == 'maxpool3s2'
+                          and second[1] == first[9])
+        # network input: NHWC8 (layout 1 of fm_roi_resize_norm) or, for the fused stem, NHWC4 inside a zero border
+        self.inp_layout = 2 if self.fuse_stem else 1
+        if self.fuse_stem:
+            self.inp = torch.zeros(B, H + 8, W + 8, 4, dtype=torch.float16, device=dev)
+        else:
+            self.inp = torch.zeros(B, H, W, IN_C_PAD, dtype=torch.float16, device=dev)
         self.out = torch.zeros(B, feature_dim, dtype=torch.float32, device=dev)
         self.n_dev = None
         # last use of every symbolic buffer -> simple size-keyed recycling
@@ -272,15 +290,9 @@ class OSNetEngine(_Net):
         self.gate_tmp = torch.zeros(4 * B, 512, dtype=torch.float32, device=dev)
         self._params = params
         fused_add = {}
-        # FM_OSB_FUSED=0 falls back to one launch per layer (r01 path); default: one fm_osb_streams launch per OSBlock
-        # for conv1 + the four Lite-3x3 streams (csrc/osnet_fused.cu)
-        self.fuse_osb = os.environ.get("FM_OSB_FUSED", "1") != "0" and use_tc
         self.n_osb = 0
         skip_until = -1
         pooled_by_tail = {}
-        # FM_OSB_FUSED=0 falls back to one launch per layer (r01 path); default: one fm_osb_streams launch per OSBlock
-        # for conv1 + the four Lite-3x3 streams (csrc/osnet_fused.cu)
-        self.fuse_osb = os.environ.get("FM_OSB_FUSED", "1") != "0" and use_tc
         self.n_osb = 0
         skip_until = -1
         pooled_by_tail = {}
@@ -290,6 +302,21 @@ class OSNetEngine(_Net):
         for k, op in enumerate(self.ops):
             kind = op[0]
             if k <= skip_until:
+                continue
+            if k == 0 and self.fuse_stem:
+                from .packing import pack_b_sw128
+                w7, b7 = self.weights[op[1]]                        # [64][7][7][3]
+                wk = np.zeros((64, 8, 8, 4), np.float32)
+                wk[:, :7, 1:8, :3] = w7
+                img = torch.as_tensor(pack_b_sw128(wk.reshape(64, 256))).to(dev)
+                b_d = torch.as_tensor(np.ascontiguousarray(b7, np.float32)).to(dev)
+                y = alloc(B * 64 * 32 * 64)
+                self._keep += [img, b_d]
+                self._add('fm_osnet_stem', ptr(self.inp), B, ptr(img), ptr(b_d), ptr(y))
+                self.n_tc += 1
+                self.layer_bytes += 2 * (B * (H + 8) * (W + 8) * 4 + B * 64 * 32 * 64)
+                live[self.ops[1][2]] = (y, 64, 64, 32)
+                skip_until = 1
                 continue
             if kind == 'conv' and self.fuse_osb and op[1].endswith('.conv1'):
                 blk = self._match_osblock(k)
@@ -428,6 +455,7 @@ class OSNetEngine(_Net):
                 d.gap_part = gap.data_ptr()
                 d.gw1, d.gb1, d.gw2, d.gb2 = (t_.data_ptr() for t_ in (gw1, gb1, gw2, gb2))
                 d.wimg, d.bias, d.out = img_d.data_ptr(), bias_d.data_ptr(), y.data_ptr()
+                d.gate_scratch = self.gate_tmp.data_ptr()
                 self._keep += [d, img_d, bias_d]
                 self._add('fm_osb_merge', C.byref(d))
                 self.n_tc += 1
@@ -553,6 +581,15 @@ class OSNetEngine(_Net):
         if kind == 'fc':
             return [op[4]]
         return []
+
+    def load_nhwc8(self, x):
+        """Copies crops given as [n][256][128][>= 3] fp16 (RGB first) into the engine's input buffer, whatever its
+        layout (tests and tools; the product path writes the buffer with fm_roi_resize_norm)."""
+        n = x.shape[0]
+        if self.inp_layout == 2:
+            self.inp[:n, 4:-4, 4:-4, :3].copy_(x[..., :3])
+        else:
+            self.inp[:n].copy_(x)
 
     def forward(self, n=None):
         """Runs the recorded network on self.inp (all max_batch rows; rows >= n are don't-care)."""

@@ -35,9 +35,10 @@ class FeatureExtractor:
         self._out = None
 
     def _engine(self, n):
-        """Engines are planned per batch bucket (multiples of 32) so small frames do not pay for max_crops."""
+        """Engines are planned per batch bucket (multiples of 8 crops): a frame pays for its own crops, not for
+        max_crops."""
         from .engine import build_reid_engine
-        b = max(32, -(-n // 32) * 32)
+        b = max(8, -(-n // 8) * 8)
         if b not in self._engines:
             self._engines[b] = build_reid_engine(self.model, max_batch=b, use_tc=self._use_tc,
                                                  use_graph=self._use_graph)
@@ -73,8 +74,8 @@ class FeatureExtractor:
         self._tlbr_host[:n] = torch.as_tensor(tlbrs)
         self._tlbr_dev[:n].copy_(self._tlbr_host[:n], non_blocking=True)
         c, ih, iw = self.model.INPUT_SHAPE
-        rc = self._lib.fm_roi_resize_norm(ptr(frame_dev), w, h, ptr(self._tlbr_dev), None, n, iw, ih, 1,
-                                          ptr(eng.inp), stream_ptr())
+        rc = self._lib.fm_roi_resize_norm(ptr(frame_dev), w, h, ptr(self._tlbr_dev), None, n, iw, ih,
+                                          eng.inp_layout, ptr(eng.inp), stream_ptr())
         _lib.check(rc, "fm_roi_resize_norm")
         self._out = eng.forward(n)
 

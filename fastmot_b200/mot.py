@@ -41,7 +41,8 @@ class MOT:
                  visualizer_cfg=None,
                  draw=False,
                  detections_override=None,
-                 embeddings_override=None):
+                 embeddings_override=None,
+                 embeddings_tap=None):
         self.size = size
         self.detector_type = DetectorType[detector_type.upper()]
         assert detector_frame_skip >= 1
@@ -81,6 +82,8 @@ class MOT:
         self.detections_override = detections_override
         # Optional callable (frame_id, detections) -> (N, dim) embeddings replacing the ReID OUTPUT (parity rigs).
         self.embeddings_override = embeddings_override
+        # Optional observer (frame_id, detections, embeddings): sees what the association stage is fed (parity rigs).
+        self.embeddings_tap = embeddings_tap
 
     def visible_tracks(self):
         """Confirmed and active tracks (mot.py:103-112)."""
@@ -132,6 +135,8 @@ class MOT:
                     embeddings = embeddings[0]
                 if self.embeddings_override is not None:
                     embeddings = self.embeddings_override(self.frame_count, detections)
+                if self.embeddings_tap is not None:
+                    self.embeddings_tap(self.frame_count, detections, embeddings)
             with Profiler('assoc'):
                 self.tracker.update(self.frame_count, detections, embeddings)
         else:

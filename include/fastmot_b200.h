@@ -140,7 +140,9 @@ int fm_letterbox_preproc(const unsigned char* frame, int src_w, int src_h, int d
 /* FeatureExtractor.extract_async preprocessing (fastmot/feature_extractor.py:48-60, 84-98; rect.py:92-97) for all
  * crops in one launch: integer-truncated clamp crop, OpenCV INTER_LINEAR 8-bit fixed-point resize to
  * out_w x out_h, BGR->RGB, (x/255 - mean)/std.  n = min(*n_dev, n_max) if n_dev != NULL else n_max.
- * layout as above; output is [n][3][out_h][out_w] f32 or [n][out_h][out_w][8] f16. */
+ * layout as above; output is [n][3][out_h][out_w] f32 or [n][out_h][out_w][8] f16; layout 2: fp16
+ * [n][out_h + 8][out_w + 8][4] with the crop at (+4, +4) inside a border the CALLER zeroed once (the zero padding of
+ * the OSNet 7x7 stem, fm_osnet_stem). */
 int fm_roi_resize_norm(const unsigned char* frame, int src_w, int src_h, const double* tlbrs, const int* n_dev,
                        int n_max, int out_w, int out_h, int layout, void* out, void* stream);
 
@@ -336,6 +338,12 @@ int fm_osb_streams(const FmOsbStreams* h_desc, void* stream);
 /* number of strips per crop kernel S uses for this geometry (0 = unsupported) */
 int fm_osb_streams_strips(int h, int w, int mid);
 
+/* OSNet stem in one launch (csrc/osnet_stem.cu): conv 7x7 / 2 (3 -> 64) + bias + ReLU + max-pool 3x3 / 2.
+ * x: fp16 [n][264][136][4] (fm_roi_resize_norm layout 2: 256 x 128 crop at (+4, +4), zero border); wimg:
+ * pack_b_sw128 image of W[64][256], W[o][r * 32 + j * 4 + c] = w[o][r][j - 1][c] (zero for j = 0, c = 3, r = 7);
+ * bias fp32 [64]; out: fp16 [n][64][32][64] NHWC. */
+int fm_osnet_stem(const void* x, int n, const void* wimg, const float* bias, void* out, void* stream);
+
 /* Kernel G: the rest of the OSBlock in one launch (torchreid OSBlock: gate, conv3, downsample, residual, ReLU):
  *   out = relu(conv3(sum_s gate(tail_s) * tail_s) + b3 + identity),  identity = res (cin == cout) or downsample(x).
  * tails / gap_part: outputs of fm_osb_streams; gw1 [cr][mid], gb1 [cr], gw2 [mid][cr], gb2 [mid]: gate FCs (fp32);
@@ -353,6 +361,7 @@ typedef struct FmOsbMerge {
     const void* x;
     const void* res;
     void* out;
+    float* gate_scratch;        /* 4 * n * mid floats: the gates, written by a small FC kernel launched first */
 } FmOsbMerge;
 int fm_osb_merge(const FmOsbMerge* h_desc, void* stream);
 int fm_osb_merge_ncta(int mid, int cout);

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from fastmot_b200.engine import OSNetEngine
 eng = OSNetEngine(1.0, max_batch=224, use_graph=False)
-eng.inp.normal_()
+eng.load_nhwc8(torch.randn(224, 256, 128, 8, device='cuda').half())
 for _ in range(3):
     eng.forward()
 torch.cuda.synchronize()

@@ -13,7 +13,7 @@ batch = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 width = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 eager = "--eager" in sys.argv
 eng = OSNetEngine(width, max_batch=batch, use_graph=not eager)
-eng.inp.copy_(torch.randn_like(eng.inp) * 0.5)
+eng.load_nhwc8(torch.randn(batch, 256, 128, 8, device='cuda').half() * 0.5)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for _ in range(2 if eager else 5):
     eng.forward()

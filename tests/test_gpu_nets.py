@@ -147,7 +147,8 @@ def test_yolov4_tiny_engine_vs_oracle():
     assert eng.n_tc + eng.n_simt == 21
 
 
-@pytest.mark.parametrize("name,hw", [("yolov4-csp", (256, 256)), ("yolov4-p5", (256, 256)), ("yolov4", (256, 256))])
+@pytest.mark.parametrize("name,hw", [("yolov4-csp", (256, 256)), ("yolov4-p5", (256, 256)), ("yolov4", (256, 256)),
+                                     ("yolov4-csp", (640, 640))])      # the benchmarked detector shape
 def test_deep_yolo_engine_layerwise(name, hw):
     """Deep random-weight nets amplify rounding noise end to end (no trained BN statistics), so every layer is
     checked against fp32 torch applied to the ENGINE's own input for that layer (teacher forcing): covers each
@@ -225,7 +226,7 @@ def test_osnet_engine_vs_oracle(width):
     x = torch.randn(6, 3, 256, 128, generator=g)
     inp = torch.zeros(6, 256, 128, 8, dtype=torch.float16)
     inp[..., :3] = x.permute(0, 2, 3, 1).half()
-    eng.inp.copy_(inp.cuda())
+    eng.load_nhwc8(inp.cuda())
     got = eng.forward().cpu()
     want = nets.run_osnet(eng.ops, eng.weights, inp[..., :3].float().permute(0, 3, 1, 2), nets.fp16_roundtrip)
     assert got.shape == want.shape == (6, 512)

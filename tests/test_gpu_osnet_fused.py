@@ -129,7 +129,7 @@ def test_osnet_x1_fused_engine_vs_oracle_and_unfused(batch, graph, monkeypatch):
     inp[..., :3] = x.permute(0, 2, 3, 1).half()
     eng = OSNetEngine(1.0, max_batch=batch, use_graph=graph)
     assert eng.n_osb == 6
-    eng.inp.copy_(inp.cuda())
+    eng.load_nhwc8(inp.cuda())
     got = eng.forward().clone()
     if graph:
         for _ in range(2):
@@ -139,7 +139,7 @@ def test_osnet_x1_fused_engine_vs_oracle_and_unfused(batch, graph, monkeypatch):
     monkeypatch.setenv("FM_OSB_FUSED", "0")
     ref_eng = OSNetEngine(1.0, weights=eng.weights, max_batch=batch, use_graph=False)
     assert ref_eng.n_osb == 0
-    ref_eng.inp.copy_(inp.cuda())
+    ref_eng.load_nhwc8(inp.cuda())
     unfused = ref_eng.forward().cpu()
     assert float((got - unfused).abs().max()) < 5e-3, float((got - unfused).abs().max())
     nb = min(batch, 8)         # the CPU oracle is slow: first crops only
@@ -182,6 +182,8 @@ def run_osb_merge(tails, gw, w3, b3, wd=None, bd=None, x=None, res=None):
     d.gap_part = gap.data_ptr()
     d.gw1, d.gb1, d.gw2, d.gb2 = (g.data_ptr() for g in gws)
     d.wimg, d.bias, d.out = img.data_ptr(), bias_d.data_ptr(), out.data_ptr()
+    scratch = torch.zeros(4 * n * mid, dtype=torch.float32, device=dev)
+    d.gate_scratch = scratch.data_ptr()
     d.x = x.data_ptr() if x is not None else None
     d.res = res.data_ptr() if res is not None else None
     _lib.check(lib.fm_osb_merge(C.byref(d), stream_ptr()), "fm_osb_merge")
@@ -224,3 +226,33 @@ def test_osb_merge_vs_torch(w, mid, h, cin, cout, n):
     assert torch.isfinite(gotc).all()
     err = float((gotc - want).abs().max()) / (float(want.abs().max()) + 1e-6)
     assert err < 4e-3, err
+
+
+@pytest.mark.parametrize("n", [1, 5])
+def test_osnet_stem_vs_torch(n):
+    """Fused 7x7/2 conv + ReLU + 3x3/2 max-pool (TMA 5-D window tiles) against fp32 torch."""
+    from fastmot_b200 import _lib
+    from fastmot_b200.devmem import ptr, stream_ptr
+    from fastmot_b200.packing import pack_b_sw128
+    lib = _lib.require_device()
+    rng = np.random.default_rng(7)
+    w7 = rng.normal(0, np.sqrt(2.0 / 147), (64, 7, 7, 3)).astype(np.float32)
+    b7 = rng.normal(0, 0.05, 64).astype(np.float32)
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n, 256, 128, 3, generator=g).half()
+    xin = torch.zeros(n, 264, 136, 4, dtype=torch.float16)
+    xin[:, 4:-4, 4:-4, :3] = x
+    wk = np.zeros((64, 8, 8, 4), np.float32)
+    wk[:, :7, 1:8, :3] = w7
+    img = torch.as_tensor(pack_b_sw128(wk.reshape(64, 256))).cuda()
+    out = torch.full((n, 64, 32, 64), float('nan'), dtype=torch.float16, device="cuda")
+    xin_d, b_d = xin.cuda(), torch.as_tensor(b7).cuda()
+    _lib.check(lib.fm_osnet_stem(ptr(xin_d), n, ptr(img), ptr(b_d), ptr(out), stream_ptr()), "fm_osnet_stem")
+    torch.cuda.synchronize()
+    wt = _h(torch.as_tensor(w7)).permute(0, 3, 1, 2).contiguous()
+    y = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), wt, torch.as_tensor(b7), stride=2, padding=3))
+    want = F.max_pool2d(_h(y), 3, 2, 1).permute(0, 2, 3, 1)
+    got = out.float().cpu()
+    assert torch.isfinite(got).all()
+    err = float((got - want).abs().max()) / (float(want.abs().max()) + 1e-6)
+    assert err < 3e-3, err

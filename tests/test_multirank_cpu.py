@@ -18,7 +18,8 @@ def _worker(rank, world, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sys.path.insert(0, ROOT)
     import bench
-    scene, frames = bench.make_frames(rank, 2)
+    scene = bench.make_scene(bench.CONFIGS[3], rank)
+    frames = [scene.frame(t) for t in range(2)]
     ms = bench.reduce_max_ms(10.0 + 5.0 * rank, world, torch.device("cpu"))
     dist.barrier()
     out[rank] = (float(scene.x0[0] + scene.vel[0, 0]), int(frames[1].sum() % 1000003), ms)
