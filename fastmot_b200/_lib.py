@@ -62,7 +62,7 @@ SIGNATURES = {
     "fm_memcpy_async": (c_i, [c_p, c_p, c_ll, c_p]),
     "fm_host_is_pinned": (c_i, [c_p]),
     "fm_launch_count": (c_ll, []),
-    "fm_kalman_step_batched": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p,
+    "fm_kalman_step_batched": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
                                       C.POINTER(FmKalmanParams), c_d, c_d, c_p, c_p, c_p]),
     "fm_kalman_create_batched": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, C.POINTER(FmKalmanParams), c_p]),
     "fm_motion_distance": (c_i, [c_p, c_p, c_p, c_i, c_p, c_i, C.POINTER(FmKalmanParams), c_p, c_p]),

@@ -452,7 +452,7 @@ extern "C" int fm_lsa(const double* cost, int nr, int nc, int* col4row, int* sta
     size_t bytes = lsa_bytes(a, b);
     int use_smem = bytes <= 46 * 1024;
     FM_REQUIRE(use_smem || workspace, "fm_lsa: workspace required for this size");
-    if (b > 48)   // one thread per column: the per-step scan, resets and dual updates run CTA-wide
+    if (b > 48 || getenv("FM_LSA_V1") == nullptr)   // <= 256 columns: one warp, state in registers (assoc_lsa_block.cu)
         fm_launch_lsa_block(cost, nr, nc, col4row, status, (unsigned char*)workspace, use_smem, bytes,
                             (cudaStream_t)stream);
     else

@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(64) kalman_kernel(double* __restrict__ mean_po
                                                      const int* __restrict__ slots, int n, int flags,
                                                      const double* __restrict__ Hm,
                                                      const int* __restrict__ h_ok,
+                                                     const int* __restrict__ hold,
                                                      const double* __restrict__ meas,
                                                      const unsigned char* __restrict__ has_meas,
                                                      const double* __restrict__ mult_num,
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(64) kalman_kernel(double* __restrict__ mean_po
     const int i = blockIdx.x;
     if (i >= n) return;
     if (h_ok && *h_ok == 0) return;  // camera motion estimation failed: caller clears all tracks
+    if (hold && *hold != 0) return;  // the KLT box rounds have not reached their fixed point: caller reruns
     const int t = threadIdx.x;
     const int slot = slots[i];
     P[t] = cov_pool[(size_t)slot * 64 + t];
@@ -286,7 +288,7 @@ extern "C" int fm_motion_distance(const double* mean_pool, const double* cov_poo
 
 extern "C" int fm_kalman_step_batched(double* mean_pool, double* cov_pool, double* tlbr_pool, const int* slots, int n,
                                       int flags,
-                                      const double* homography, const int* h_ok, const double* meas,
+                                      const double* homography, const int* h_ok, const int* hold, const double* meas,
                                       const unsigned char* has_meas, const double* mult_num,
                                       const double* mult_den_pool, const FmKalmanParams* params, double frame_w,
                                       double frame_h, double* out_tlbr, unsigned char* out_lost, void* stream) {
@@ -295,7 +297,7 @@ extern "C" int fm_kalman_step_batched(double* mean_pool, double* cov_pool, doubl
     FM_REQUIRE(!(flags & FM_KF_UPDATE) || meas, "fm_kalman_step_batched: UPDATE needs measurements");
     if (n <= 0) return FM_OK;
     kalman_kernel<<<n, 64, 0, (cudaStream_t)stream>>>(mean_pool, cov_pool, tlbr_pool, slots, n, flags, homography, h_ok,
-                                                      meas,
+                                                      hold, meas,
                                                       has_meas, mult_num, mult_den_pool, *params, frame_w, frame_h,
                                                       out_tlbr, out_lost);
     FM_CHECK_LAUNCH("fm_kalman_step_batched");

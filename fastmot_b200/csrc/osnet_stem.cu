@@ -5,10 +5,11 @@
 // (fm_roi_resize_norm layout 2).  With 8 bytes per pixel a kernel row of an output pixel is ONE 64-byte run
 // (8 pixels x 4 channels, the first pixel gets zero weights), so the implicit-GEMM A tile needs no gather:
 //     A[m = (oy, ox)][k = r * 32 + j * 4 + c] = in[2 oy + 1 + r][2 ox + j][c]          r = 0..7, j = 0..7
-// is a 5-D TMA tensor (32 elements | 2 kernel rows | 64 ox, stride 16 B | oy, stride 2 rows | crop) whose box
-// {32, 2, 64, 2, 1} lands as a [128 pixels][64 K] tile, 128-byte swizzled: four TMA loads per 128 output pixels
-// (two conv rows), K = 256 (r = 7 and j = 0 carry zero weights).  tcgen05.mma 128 x 64 x 16, accumulators double
-// buffered in TMEM; weights (32 KB image) stay in shared memory for the whole CTA.
+// is a 5-D TMA tensor (32 elements | kernel row r | 64 ox, stride 16 B | oy, stride 2 rows | crop) whose box
+// {32, 1, 64, 2, 1} lands as a [128 pixels][32 K] tile of 64-byte rows, 64-byte swizzled (a 64-byte inner box cannot
+// share a 128-byte swizzle row with a second kernel row: TMA pads it): seven 8 KB TMA loads per 128 output pixels
+// (two conv rows), K = 7 x 32 (j = 0 carries zero weights).  tcgen05.mma 128 x 64 x 16 on SWIZZLE_64B descriptors,
+// accumulators double buffered in TMEM; the weights (28 KB image) stay in shared memory for the whole CTA.
 // One CTA = NP pooled rows of one crop: it walks the conv-row pairs ("tiles") top to bottom, keeps the last three
 // conv rows (ReLU'd fp16) in shared memory and emits one pooled row per tile.  Post-ReLU values are >= 0, so the
 // max-pool padding is a plain zero.
@@ -19,7 +20,8 @@ namespace {
 
 using namespace tc;
 
-constexpr int STEM_NS = 3;             // TMA ring depth (tiles of 4 x 16 KB = 64 KB would be too much: per K slice)
+constexpr int STEM_NS = 6;             // TMA ring depth (8 KB stages, one kernel row each)
+constexpr int STEM_KR = 7;             // kernel rows
 constexpr int STEM_ROWP = 64 * 128 + 64 * 16;   // one conv row: 64 px x (128 B + 16 B pad)
 
 __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
@@ -31,18 +33,20 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+__device__ float* g_stem_dbg = nullptr;        // debugging aid (scripts/debug_stem.py): raw accumulators + A slices of CTA 0, tile 0
+
 struct StemArgs {
     int n, np, bands;            // crops, pooled rows per CTA, CTAs per crop
-    const uint8_t* wimg;         // 4 slices of [64 x 128 B]
+    const uint8_t* wimg;         // 7 slices (kernel rows) of [64 x 64 B], SWIZZLE_64B
     const float* bias;           // [64]
     __half* out;                 // [n][64][32][64]
 };
 
 __global__ void __launch_bounds__(288, 2) osnet_stem_kernel(const __grid_constant__ CUtensorMap map_x, StemArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* s_w = smem;                                  // 32 KB weights
-    uint8_t* s_ring = smem + 32768;                       // STEM_NS x 16 KB A slices
-    uint8_t* s_rows = s_ring + STEM_NS * 16384;           // 3 conv rows, pixel-major, 144 B per pixel
+    uint8_t* s_w = smem;                                  // 7 x 4 KB weights (32 KB reserved)
+    uint8_t* s_ring = smem + 32768;                       // STEM_NS x 8 KB A slices
+    uint8_t* s_rows = s_ring + STEM_NS * 8192;            // 3 conv rows, pixel-major, 144 B per pixel
     __shared__ uint64_t w_full, ring_full[STEM_NS], ring_empty[STEM_NS], acc_full[2], acc_empty[2];
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -71,36 +75,42 @@ __global__ void __launch_bounds__(288, 2) osnet_stem_kernel(const __grid_constan
     if (warp == 8) {
         const bool leader = lane == 0;
         if (leader) {
-            mbar_expect_tx(&w_full, 32768);
-            bulk_load(s_w, a.wimg, 32768, &w_full);
+            mbar_expect_tx(&w_full, STEM_KR * 4096);
+            bulk_load(s_w, a.wimg, STEM_KR * 4096, &w_full);
         }
         fm_pdl_wait();
         const uint32_t idesc = idesc_f16(64);
-        const int iters = ntiles * 4;
+        const int iters = ntiles * STEM_KR;
         auto issue = [&](int i) {
-            const int st = i % STEM_NS, t = t0 + (i >> 2), ks = i & 3;
+            const int st = i % STEM_NS, t = t0 + i / STEM_KR, kr = i % STEM_KR;
             if (i >= STEM_NS) mbar_wait(&ring_empty[st], (uint32_t)((i / STEM_NS - 1) & 1));
             if (leader) {
-                mbar_expect_tx(&ring_full[st], 16384);
-                tma_load_5d(s_ring + st * 16384, &map_x, &ring_full[st], 0, 2 * ks, 0, 2 * t, crop);
+                mbar_expect_tx(&ring_full[st], 8192);
+                tma_load_5d(s_ring + st * 8192, &map_x, &ring_full[st], 0, kr, 0, 2 * t, crop);
             }
         };
         for (int i = 0; i < STEM_NS - 1 && i < iters; ++i) issue(i);
         mbar_wait(&w_full, 0);
         for (int i = 0; i < iters; ++i) {
             if (i + STEM_NS - 1 < iters) issue(i + STEM_NS - 1);
-            const int st = i % STEM_NS, tl = i >> 2, ks = i & 3, ai = tl & 1;
+            const int st = i % STEM_NS, tl = i / STEM_KR, ks = i % STEM_KR, ai = tl & 1;
             if (ks == 0 && tl >= 2) mbar_wait(&acc_empty[ai], (uint32_t)(((tl >> 1) - 1) & 1));
             mbar_wait(&ring_full[st], (uint32_t)((i / STEM_NS) & 1));
             fence_after();
-            const uint32_t sa = smem_u32(s_ring + st * 16384), sb = smem_u32(s_w) + ks * 8192;
+            if (g_stem_dbg && blockIdx.x == 0 && tl == 0) {
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(s_ring + st * 8192);
+                uint32_t* dstw = reinterpret_cast<uint32_t*>(g_stem_dbg + 128 * 64) + ks * 2048;
+                for (int w = lane; w < 2048; w += 32) dstw[w] = src[w];
+                __syncwarp();
+            }
+            const uint32_t sa = smem_u32(s_ring + st * 8192), sb = smem_u32(s_w) + ks * 4096;
             if (leader) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    mma_ss(tmem + ai * 64, smem_desc_sw128(sa + k * 32), smem_desc_sw128(sb + k * 32), idesc,
+                for (int k = 0; k < 2; ++k)
+                    mma_ss(tmem + ai * 64, smem_desc_sw64(sa + k * 32), smem_desc_sw64(sb + k * 32), idesc,
                            (ks > 0 || k > 0) ? 1u : 0u);
                 commit(&ring_empty[st]);
-                if (ks == 3) commit(&acc_full[ai]);
+                if (ks == STEM_KR - 1) commit(&acc_full[ai]);
             }
             __syncwarp();
         }
@@ -120,6 +130,8 @@ __global__ void __launch_bounds__(288, 2) osnet_stem_kernel(const __grid_constan
             uint32_t r[32];
             tmem_ld32(lane_base + ai * 64 + hsel * 32, r);
             tmem_ld_wait();
+            if (g_stem_dbg && blockIdx.x == 0 && tl == 0)
+                for (int e = 0; e < 32; ++e) g_stem_dbg[(q * 32 + lane) * 64 + hsel * 32 + e] = __uint_as_float(r[e]);
             fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[ai]);
@@ -170,8 +182,14 @@ __global__ void __launch_bounds__(288, 2) osnet_stem_kernel(const __grid_constan
 
 }  // namespace
 
-// x: fp16 [n][264][136][4] (fm_roi_resize_norm layout 2, zero border); wimg: pack_b_sw128 image of the [64][256]
-// weight matrix W[cout][r * 32 + j * 4 + c] = w[cout][r][j - 1][c] (zero for j == 0, c == 3, r == 7); bias fp32 [64];
+extern "C" int fm_osnet_stem_set_debug(void* p) {      // not part of the public header
+    float* q = (float*)p;
+    cudaMemcpyToSymbol(g_stem_dbg, &q, sizeof(q));
+    return FM_OK;
+}
+
+// x: fp16 [n][264][136][4] (fm_roi_resize_norm layout 2, zero border); wimg: pack_b_sw64 image of the [64][224]
+// weight matrix W[cout][r * 32 + j * 4 + c] = w[cout][r][j - 1][c] (zero for j == 0 and c == 3); bias fp32 [64];
 // out: fp16 [n][64][32][64] NHWC (after ReLU and the 3x3 / 2 max-pool).
 extern "C" int fm_osnet_stem(const void* x, int n, const void* wimg, const float* bias, void* out, void* stream) {
     if (n <= 0) return FM_OK;
@@ -181,11 +199,11 @@ extern "C" int fm_osnet_stem(const void* x, int n, const void* wimg, const float
     CUtensorMap map;
     cuuint64_t dims[5] = {32, 8, 64, 128, (cuuint64_t)n};
     cuuint64_t strides[4] = {P * 2, 16, 2 * P * 2, 264 * P * 2};    // bytes, dims 1..4
-    cuuint32_t box[5] = {32, 2, 64, 2, 1};
+    cuuint32_t box[5] = {32, 1, 64, 2, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     void* base = (void*)((const __half*)x + P);           // first conv row reads padded row 1 (= image row -3)
     CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, base, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char buf[128];
@@ -196,7 +214,7 @@ extern "C" int fm_osnet_stem(const void* x, int n, const void* wimg, const float
     StemArgs a;
     a.n = n; a.np = 8; a.bands = 64 / a.np;
     a.wimg = (const uint8_t*)wimg; a.bias = bias; a.out = (__half*)out;
-    const int smem = 32768 + STEM_NS * 16384 + 3 * STEM_ROWP;
+    const int smem = 32768 + STEM_NS * 8192 + 3 * STEM_ROWP;
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(osnet_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -101,6 +101,16 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
+// K-major, SWIZZLE_64B: rows of 64 bytes (32 fp16 of K), 8-row groups 512 bytes apart, 16-byte chunk index XOR (row / 2) % 4
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
 // kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, M = 128, N = n
 __device__ __forceinline__ uint32_t idesc_f16(int n) {
     uint32_t d = 0;

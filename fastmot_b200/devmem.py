@@ -118,13 +118,17 @@ class FrameUploader:
         self.host_np = [t.numpy() for t in self.host]
         self.events = [None] * depth
         self.cur = 0
+        # read-ahead (GPU-resident ingest, role of the reference's VideoIO frame queue, fastmot/videoio.py:125-142):
+        # prefetch(frame) starts the H2D copy of a FUTURE frame on a dedicated upload stream while the current step
+        # computes; upload() of that same frame then only waits for the copy's event.
+        self._up_stream = torch.cuda.Stream(device=device)
+        self._prefetched = None            # (key, slot, event)
 
-    def upload(self, frame):
-        frame = np.ascontiguousarray(frame)
-        if frame.shape != self.shape or frame.dtype != np.uint8:
-            raise ValueError(f"frame must be uint8 {self.shape}, got {frame.dtype} {frame.shape}")
-        k = self.cur
-        self.cur = (k + 1) % len(self.dev)
+    @staticmethod
+    def _key(frame):
+        return (frame.ctypes.data, frame.shape)
+
+    def _copy(self, frame, k, stream):
         src = frame.ctypes.data
         if not self._lib.fm_host_is_pinned(C.c_void_p(src)):
             ev = self.events[k]
@@ -132,8 +136,35 @@ class FrameUploader:
                 ev.synchronize()
             np.copyto(self.host_np[k], frame)
             src = self.host[k].data_ptr()
-        self._lib.fm_memcpy_async(C.c_void_p(self.dev[k].data_ptr()), C.c_void_p(src), self.nbytes, stream_ptr())
+        self._lib.fm_memcpy_async(C.c_void_p(self.dev[k].data_ptr()), C.c_void_p(src), self.nbytes,
+                                  C.c_void_p(stream.cuda_stream))
         ev = torch.cuda.Event()
-        ev.record()
+        ev.record(stream)
         self.events[k] = ev
+        return ev
+
+    def prefetch(self, frame):
+        """Starts the upload of a frame that a later upload() call will ask for (the same ndarray)."""
+        frame = np.ascontiguousarray(frame)
+        if frame.shape != self.shape or frame.dtype != np.uint8:
+            raise ValueError(f"frame must be uint8 {self.shape}, got {frame.dtype} {frame.shape}")
+        k = self.cur
+        self.cur = (k + 1) % len(self.dev)
+        # the slot's previous contents may still be read by kernels of the main stream
+        self._up_stream.wait_stream(torch.cuda.current_stream())
+        ev = self._copy(frame, k, self._up_stream)
+        self._prefetched = (self._key(frame), k, ev)
+
+    def upload(self, frame):
+        frame = np.ascontiguousarray(frame)
+        if self._prefetched is not None and self._prefetched[0] == self._key(frame):
+            _, k, ev = self._prefetched
+            self._prefetched = None
+            torch.cuda.current_stream().wait_event(ev)
+            return self.dev[k]
+        if frame.shape != self.shape or frame.dtype != np.uint8:
+            raise ValueError(f"frame must be uint8 {self.shape}, got {frame.dtype} {frame.shape}")
+        k = self.cur
+        self.cur = (k + 1) % len(self.dev)
+        self._copy(frame, k, torch.cuda.current_stream())
         return self.dev[k]

@@ -304,11 +304,11 @@ class OSNetEngine(_Net):
             if k <= skip_until:
                 continue
             if k == 0 and self.fuse_stem:
-                from .packing import pack_b_sw128
+                from .packing import pack_b_sw64
                 w7, b7 = self.weights[op[1]]                        # [64][7][7][3]
-                wk = np.zeros((64, 8, 8, 4), np.float32)
-                wk[:, :7, 1:8, :3] = w7
-                img = torch.as_tensor(pack_b_sw128(wk.reshape(64, 256))).to(dev)
+                wk = np.zeros((64, 7, 8, 4), np.float32)
+                wk[:, :, 1:8, :3] = w7
+                img = torch.as_tensor(pack_b_sw64(wk.reshape(64, 224))).to(dev)
                 b_d = torch.as_tensor(np.ascontiguousarray(b7, np.float32)).to(dev)
                 y = alloc(B * 64 * 32 * 64)
                 self._keep += [img, b_d]

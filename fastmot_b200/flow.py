@@ -127,6 +127,11 @@ class Flow:
         self.est_boxes = torch.zeros(2 * max_tracks * 5, dtype=i32, device=dev)
         self.sig = torch.zeros(max_tracks, dtype=torch.int64, device=dev)
         self._h_flags = torch.zeros(32, dtype=i32).pin_memory()
+        # True (set by MultiTracker): predict_device returns without any host sync; the caller checks the round flags
+        # together with its own read-back (check_flags / finish_rounds)
+        self.defer_sync = False
+        self.rounds_last = 0
+        self._affine_args = (0, size[0], size[1])
         self._h_slots = torch.zeros(max_tracks, dtype=i32).pin_memory()
         self._uploader = FrameUploader(size)
         self._side = torch.cuda.Stream()
@@ -240,28 +245,58 @@ class Flow:
                                             ptr(self.bg_kp_count), self.max_bg, s_h), "fm_ransac_homography")
         self._ev_h.record(self._side)
         self._bg_cache = None
+        # The serial "paint the predicted box, filter the next track" dependency is resolved by rounds (rounds past
+        # the fixed point exit at once on the device).  ROUNDS_AHEAD rounds are enqueued without reading anything
+        # back; the flags travel with the Kalman results (MultiTracker.apply_kalman) and `finish_rounds` runs more
+        # rounds only in the rare case the fixed point was not reached (the Kalman launch is held by the same flag).
+        self._affine_args = (n, W, H)
         rounds = 0
-        while True:
-            # rounds past the fixed point exit at once on the device, so four per host round trip cost two ~3 us
-            # launches when two would have done and save a sync + status read when they would not
-            step = 4
-            _lib.check(lib.fm_ransac_affine_partial_batch(
-                ptr(self.all_prev), ptr(self.all_cur), ptr(self.status), ptr(self.trk_begin), ptr(self.slots_dev), n,
-                step, C.c_void_p(fl + 32), None, ptr(self.est_boxes), ptr(self.sig), ptr(pool.tlbr),
-                ptr(pool.klt_tlbr), ptr(pool.klt_ok), ptr(pool.inlier_ratio), ptr(pool.kp), ptr(pool.kp_prev),
-                ptr(pool.kp_count), pool.max_kp, W, H, int(self.ransac_max_iter), float(self.ransac_conf), 3.0,
-                int(self.inlier_thresh), 10, rounds, s), "fm_ransac_affine_partial_batch")
-            rounds += step
-            lib.fm_memcpy_async(C.c_void_p(self._h_flags.data_ptr()), C.c_void_p(fl), 128, s)
-            torch.cuda.current_stream().synchronize()
-            hf = self._h_flags.numpy()
-            if hf[1] != 0:
-                raise MemoryError(f"Flow scratch/candidate overflow (code {int(hf[1])}); raise scratch_floats")
-            if n == 0 or hf[8 + ((rounds - 1) & 15)] == 0 or rounds >= 2 * max(n, 1) + 2:
-                break
-        self.rounds_last = rounds
+        for _ in range(self.ROUNDS_AHEAD // 4):
+            rounds = self._enqueue_rounds(rounds, 4)
+        if not self.defer_sync:
+            rounds = self.finish_rounds(rounds)
         main.wait_event(self._ev_h)          # H / h_ok are consumed by the Kalman step that follows
         return self._order
+
+    ROUNDS_AHEAD = 8
+
+    def _enqueue_rounds(self, rounds, step):
+        lib, pool = self._lib, self.pool
+        n, W, H = self._affine_args
+        fl = self.flags.data_ptr()
+        _lib.check(lib.fm_ransac_affine_partial_batch(
+            ptr(self.all_prev), ptr(self.all_cur), ptr(self.status), ptr(self.trk_begin), ptr(self.slots_dev), n,
+            step, C.c_void_p(fl + 32), None, ptr(self.est_boxes), ptr(self.sig), ptr(pool.tlbr),
+            ptr(pool.klt_tlbr), ptr(pool.klt_ok), ptr(pool.inlier_ratio), ptr(pool.kp), ptr(pool.kp_prev),
+            ptr(pool.kp_count), pool.max_kp, W, H, int(self.ransac_max_iter), float(self.ransac_conf), 3.0,
+            int(self.inlier_thresh), 10, rounds, stream_ptr()), "fm_ransac_affine_partial_batch")
+        self.rounds_last = rounds + step
+        return rounds + step
+
+    def hold_flag_ptr(self):
+        """Device address of the 'something changed' flag of the last enqueued round (0 = fixed point reached)."""
+        return C.c_void_p(self.flags.data_ptr() + 32 + 4 * ((self.rounds_last - 1) & 15))
+
+    def check_flags(self, hf):
+        """hf: the 32 status ints copied back.  Raises on overflow; returns True when the rounds converged."""
+        n = self._affine_args[0]
+        if hf[1] != 0:
+            raise MemoryError(f"Flow scratch/candidate overflow (code {int(hf[1])}); raise scratch_floats")
+        return n == 0 or hf[8 + ((self.rounds_last - 1) & 15)] == 0 or self.rounds_last >= 2 * max(n, 1) + 2
+
+    def finish_rounds(self, rounds=None):
+        """Blocking tail of the rounds loop: read the flags, run four more rounds while something still changes."""
+        lib = self._lib
+        rounds = self.rounds_last if rounds is None else rounds
+        fl = self.flags.data_ptr()
+        while True:
+            s = stream_ptr()
+            lib.fm_memcpy_async(C.c_void_p(self._h_flags.data_ptr()), C.c_void_p(fl), 128, s)
+            torch.cuda.current_stream().synchronize()
+            if self.check_flags(self._h_flags.numpy()):
+                break
+            rounds = self._enqueue_rounds(rounds, 4)
+        return rounds
 
     def fetch_klt_bboxes(self, order=None):
         """dict trk_id -> tlbr (f64) of the tracks whose box was predicted by the last predict_device."""

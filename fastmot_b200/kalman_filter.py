@@ -86,10 +86,10 @@ class KalmanFilter:
     # ------------------------------------------------------------------ batched device entry points
     def step_batched(self, mean_pool, cov_pool, tlbr_pool, slots_ptr, n, flags, homography=None, h_ok=None,
                      meas=None, has_meas=None, mult_num=None, mult_den_pool=None, frame_size=(0, 0),
-                     out_tlbr=None, out_lost=None):
+                     out_tlbr=None, out_lost=None, hold=None):
         """All pointer arguments are ctypes c_void_p (or None)."""
         rc = self._lib.fm_kalman_step_batched(ptr(mean_pool), ptr(cov_pool), ptr(tlbr_pool), slots_ptr, n, flags,
-                                              homography, h_ok, meas, has_meas, mult_num, mult_den_pool,
+                                              homography, h_ok, hold, meas, has_meas, mult_num, mult_den_pool,
                                               self.params, float(frame_size[0]), float(frame_size[1]),
                                               out_tlbr, out_lost, stream_ptr())
         _lib.check(rc, "fm_kalman_step_batched")

@@ -310,6 +310,47 @@ def synthetic_weights(layers, in_c, seed_base=1000, head_obj_bias=None, num_clas
     return out
 
 
+def to_cfg(layers, width, height, channels=3):
+    """Darknet .cfg text for a layer list (inverse of parse_cfg; scripts/yolo2onnx.py:86-205 reads this format).
+    Layer-index references (`layers`, `from`) are written as they are stored (relative or absolute)."""
+    out = ["[net]", f"width={width}", f"height={height}", f"channels={channels}", ""]
+    for l in layers:
+        out.append(f"[{l['type']}]")
+        for k, v in l.items():
+            if k == 'type' or k.endswith('_abs') or k in ('in_c', 'out_c'):
+                continue
+            if isinstance(v, (list, tuple)):
+                v = ",".join(str(x) for x in v)
+            out.append(f"{k}={v}")
+        out.append("")
+    return "\n".join(out)
+
+
+def save_weights(path, layers, weights, in_c):
+    """Writes {layer_index: (weight [out][kh][kw][in], bias)} (BN already folded) as a Darknet .weights file
+    (header version 0.2.5, 64-bit `seen`; per conv: BN beta, gamma, mean, var | conv bias, then [out][in][kh][kw]
+    weights -- scripts/yolo2onnx.py:283-400).  Folded weights are stored with an identity batch norm (gamma 1,
+    mean 0, var 1 - eps), so load_weights() reproduces them up to one fp32 rounding of the BN scale."""
+    import struct
+    res, _ = infer_shapes(layers, in_c, 64, 64)
+    with open(path, 'wb') as f:
+        f.write(struct.pack('<iii', 0, 2, 5))
+        f.write(struct.pack('<q', 0))
+        for i, l in enumerate(res):
+            if l['type'] != 'convolutional':
+                continue
+            w, b = weights[i]
+            cout = w.shape[0]
+            wd = np.ascontiguousarray(np.asarray(w, np.float32).transpose(0, 3, 1, 2))
+            if l.get('batch_normalize', 0):
+                for a in (np.asarray(b, np.float32), np.ones(cout, np.float32), np.zeros(cout, np.float32),
+                          np.full(cout, 1.0 - 1e-5, np.float32)):
+                    f.write(a.tobytes())
+            else:
+                f.write(np.asarray(b, np.float32).tobytes())
+            f.write(wd.tobytes())
+
+
 def load_weights(path, layers, in_c):
     """Darknet .weights -> {layer_index: (weight [out][kh][kw][in], bias)} with BN folded (eps 1e-5,
     yolo2onnx.py:419)."""

@@ -107,6 +107,13 @@ class MOT:
             dets = self.detections_override(self.frame_count)
         return dets
 
+    def prefetch(self, frame):
+        """Optional read-ahead: starts the host-to-device copy of the NEXT frame (the ndarray a later `step` call will
+        receive) on an upload stream, so it overlaps the current step's kernels (role of the reference's VideoIO
+        frame queue, fastmot/videoio.py:125-142)."""
+        if not torch.is_tensor(frame):
+            self._uploader.prefetch(frame)
+
     def step(self, frame):
         """mot.py:125-168"""
         frame_dev = frame if torch.is_tensor(frame) else self._uploader.upload(frame)

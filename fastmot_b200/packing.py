@@ -21,3 +21,20 @@ def pack_b_sw128(w):
         for c in range(8):
             img[s, rows, c ^ (rows & 7)] = blk[:, c]
     return img.reshape(-1).view(np.uint8)
+
+
+def pack_b_sw64(w):
+    """[n][k] -> K slices of 32 fp16 (64-byte rows), slice s an [n x 64 B] block at byte offset s * n * 64; 16-byte
+    chunk c of row r sits at chunk position c ^ ((r >> 1) & 3) -- the K-major SWIZZLE_64B layout (smem_desc_sw64)."""
+    w = np.asarray(w, np.float32)
+    n, k = w.shape
+    nsl = -(-k // 32)
+    wp = np.zeros((n, nsl * 32), np.float16)
+    wp[:, :k] = w.astype(np.float16)
+    img = np.zeros((nsl, n, 4, 8), np.float16)
+    rows = np.arange(n)
+    for s in range(nsl):
+        blk = wp[:, s * 32:(s + 1) * 32].reshape(n, 4, 8)
+        for c in range(4):
+            img[s, rows, c ^ ((rows >> 1) & 3)] = blk[:, c]
+    return img.reshape(-1).view(np.uint8)

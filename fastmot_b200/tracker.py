@@ -217,34 +217,47 @@ class MultiTracker:
         active_tracks = [track for track in self.tracks.values() if track.active]
         # the flow kernels leave klt boxes / flags in the pool and H / ok flag on the device; nothing is
         # synchronised here — apply_kalman consumes them and reports failure with its own D2H block.
+        self.flow.defer_sync = True
         self._klt_order = self.flow.predict_device(frame, active_tracks, self._homography_dev, self._h_ok_dev)
         self._klt_stale = True
         self._flow_pending = True
 
     def apply_kalman(self):
-        """tracker.py:164-183 as one launch + one D2H."""
+        """tracker.py:164-183 as one launch + one D2H (which also carries the flow status and the KLT round flags)."""
         n = len(self.tracks)
         items = list(self.tracks.items())
-        self.down.reset()
-        p_hok, _ = self.down.alloc((1,), np.int32)
-        p_H, _ = self.down.alloc((9,), np.float64)
-        if n:
-            slots = np.fromiter((t.slot for _, t in items), np.int32, n)
-            mult = np.fromiter((max(self.age_penalty * t.age, 1) for _, t in items), np.float64, n)
-            p_slots = self.up.put(slots)
-            p_mult = self.up.put(mult)
-            self.up.flush()
-            p_tlbr, _ = self.down.alloc((n, 4), np.float64)
-            p_lost, _ = self.down.alloc((n,), np.uint8)
-            self.kf.step_batched(self.pool.mean, self.pool.cov, self.pool.tlbr, p_slots, n,
-                                 FM_KF_WARP | FM_KF_PREDICT | FM_KF_UPDATE | FM_KF_MEAS_BY_SLOT,
-                                 homography=ptr(self._homography_dev), h_ok=ptr(self._h_ok_dev),
-                                 meas=ptr(self.pool.klt_tlbr), has_meas=ptr(self.pool.klt_ok),
-                                 mult_num=p_mult, mult_den_pool=ptr(self.pool.inlier_ratio),
-                                 frame_size=self.size, out_tlbr=p_tlbr, out_lost=p_lost)
-        # piggy-back the flow status on the same D2H
-        self._copy_status(p_hok, p_H)
-        res = self.down.fetch()
+        pending = getattr(self, '_flow_pending', False)
+
+        def launch(hold):
+            self.down.reset()
+            p_hok, _ = self.down.alloc((1,), np.int32)
+            p_H, _ = self.down.alloc((9,), np.float64)
+            p_fl, _ = self.down.alloc((32,), np.int32)
+            if n:
+                slots = np.fromiter((t.slot for _, t in items), np.int32, n)
+                mult = np.fromiter((max(self.age_penalty * t.age, 1) for _, t in items), np.float64, n)
+                p_slots = self.up.put(slots)
+                p_mult = self.up.put(mult)
+                self.up.flush()
+                p_tlbr, _ = self.down.alloc((n, 4), np.float64)
+                p_lost, _ = self.down.alloc((n,), np.uint8)
+                self.kf.step_batched(self.pool.mean, self.pool.cov, self.pool.tlbr, p_slots, n,
+                                     FM_KF_WARP | FM_KF_PREDICT | FM_KF_UPDATE | FM_KF_MEAS_BY_SLOT,
+                                     homography=ptr(self._homography_dev), h_ok=ptr(self._h_ok_dev),
+                                     meas=ptr(self.pool.klt_tlbr), has_meas=ptr(self.pool.klt_ok),
+                                     mult_num=p_mult, mult_den_pool=ptr(self.pool.inlier_ratio),
+                                     frame_size=self.size, out_tlbr=p_tlbr, out_lost=p_lost, hold=hold)
+            # piggy-back the flow status and the round flags on the same D2H
+            self._copy_status(p_hok, p_H)
+            self._lib.fm_memcpy_async(p_fl, ptr(self.flow.flags), 128, stream_ptr())
+            return self.down.fetch()
+
+        res = launch(self.flow.hold_flag_ptr() if pending else None)
+        if pending and not self.flow.check_flags(res[2]):
+            # rare: the KLT box rounds enqueued ahead did not converge; the Kalman launch was held on the device
+            self.flow.finish_rounds()
+            res = launch(None)
+        res = [res[0], res[1]] + list(res[3:])
         h_ok = int(res[0][0])
         if getattr(self, '_flow_pending', False):
             self._flow_pending = False

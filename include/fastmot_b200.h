@@ -57,10 +57,12 @@ typedef struct FmKalmanParams {
  * (flags UPDATE|MEAS_DET).  State lives in slot-indexed pools mean_pool[cap][8], cov_pool[cap][64].
  * slots[n] selects the tracks; meas[n][4], has_meas[n] (NULL = all), mult_num[n] (NULL = 1).
  * h_ok: optional device flag; if *h_ok == 0 the launch is a no-op (flow failed, tracker.py:160-162).
+ * hold: optional device flag; if *hold != 0 the launch is a no-op as well (the per-track KLT rounds that were enqueued
+ * ahead did not reach their fixed point; the caller runs more rounds and launches again).
  * out_tlbr[n][4] = round-half-even(mean[:4]) (rect.py:5-12), also stored to tlbr_pool[slot] when non-NULL;
  * out_lost[n] = ios(box, frame) < 0.5 (tracker.py:179). */
 int fm_kalman_step_batched(double* mean_pool, double* cov_pool, double* tlbr_pool, const int* slots, int n, int flags,
-                           const double* homography, const int* h_ok, const double* meas,
+                           const double* homography, const int* h_ok, const int* hold, const double* meas,
                            const unsigned char* has_meas, const double* mult_num, const double* mult_den_pool,
                            const FmKalmanParams* h_params, double frame_w, double frame_h, double* out_tlbr,
                            unsigned char* out_lost, void* stream);
@@ -340,7 +342,7 @@ int fm_osb_streams_strips(int h, int w, int mid);
 
 /* OSNet stem in one launch (csrc/osnet_stem.cu): conv 7x7 / 2 (3 -> 64) + bias + ReLU + max-pool 3x3 / 2.
  * x: fp16 [n][264][136][4] (fm_roi_resize_norm layout 2: 256 x 128 crop at (+4, +4), zero border); wimg:
- * pack_b_sw128 image of W[64][256], W[o][r * 32 + j * 4 + c] = w[o][r][j - 1][c] (zero for j = 0, c = 3, r = 7);
+ * pack_b_sw64 image of W[64][224], W[o][r * 32 + j * 4 + c] = w[o][r][j - 1][c] (zero for j = 0 and c = 3);
  * bias fp32 [64]; out: fp16 [n][64][32][64] NHWC. */
 int fm_osnet_stem(const void* x, int n, const void* wimg, const float* bias, void* out, void* stream);
 

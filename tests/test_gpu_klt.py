@@ -240,3 +240,47 @@ def test_end_to_end_tracker_with_klt_vs_reference_golden(name, n_frames):
             exact += d == 0
             total += 1
     assert exact / max(total, 1) > 0.7, exact / max(total, 1)
+
+
+@pytest.mark.parametrize("overlap,n_obj", [(False, 60), (True, 70)])
+def test_keypoint_maintenance_vs_goodFeaturesToTrack(overlap, n_obj):
+    """a10 stand-alone (fastmot/flow.py:160-184, 283-306): for every track -- nearest first, each one masking the
+    next -- the corners the GPU keeps (Shi-Tomasi min-eigenvalue, quality 0.06, minDistance from the unoccluded area,
+    ellipse filter) must be the points cv2.goodFeaturesToTrack + the reference's filters keep, in the same order."""
+    from fastmot_b200 import MultiTracker
+    from fastmot_b200.synth import SyntheticScene
+    from oracle.run import default_tracker_cfg
+    from oracle.tracker import OracleTracker
+    scene = SyntheticScene(n_obj, seed=11, label=0, overlap=overlap, dropout_frames=())
+    tl, lb, cf, _ = scene.detections(0)
+    trk = MultiTracker(scene.size, 'cosine', **default_tracker_cfg())
+    trk.reset(1 / 30)
+    trk.init(scene.frame(0), _dets(tl, lb, cf))
+    ora = OracleTracker(scene.size, 'cosine', **default_tracker_cfg())
+    ora.reset(1 / 30)
+    ora.init(scene.frame(0), tl, lb)
+    frame = scene.frame(1)
+    ora.compute_flow(frame)
+    dbg = ora.flow.debug
+    active = [t for t in trk.tracks.values() if t.active]
+    dev = trk.pool.klt_ok.device
+    h = torch.zeros(9, dtype=torch.float64, device=dev)
+    ok = torch.zeros(1, dtype=torch.int32, device=dev)
+    order = trk.flow.predict_device(torch.as_tensor(frame).cuda(), active, h, ok)
+    torch.cuda.synchronize()
+    begins = trk.flow.trk_begin[:len(order) + 1].cpu().numpy()
+    pts = trk.flow.all_prev.cpu().numpy().reshape(-1, 2)
+    ora_order = sorted(ora.tracks.values(), reverse=True)
+    assert [t.trk_id for t in ora_order] == [tid for tid, _ in order]
+    same_set = same_order = 0
+    for i, (tid, _) in enumerate(order):
+        got = pts[begins[i]:begins[i + 1]]
+        want = dbg['all_prev'][dbg['begins'][i]:dbg['ends'][i]]
+        gs, ws = set(map(tuple, got.tolist())), set(map(tuple, want.tolist()))
+        same_set += gs == ws
+        same_order += got.shape == want.shape and np.array_equal(got, want)
+    assert same_set == len(order), (same_set, len(order))
+    assert same_order == len(order), (same_order, len(order))
+    # background FAST points follow the per-track blocks
+    bg_got = pts[begins[len(order)]:begins[len(order)] + (len(dbg['all_prev']) - dbg['bg_begin'])]
+    assert np.array_equal(bg_got, dbg['all_prev'][dbg['bg_begin']:])

@@ -274,3 +274,33 @@ def test_yolo_detector_end_to_end_vs_oracle_pipeline():
     if len(want[0]) and len(got):
         d = np.abs(got.tlbr[:, None, :] - want[0][None, :, :]).max(-1)
         assert (d.min(1) <= 2).mean() > 0.8
+
+
+def test_darknet_cfg_and_weights_files_through_the_gpu_engine(tmp_path):
+    """a Darknet .cfg + .weights pair on disk (written from the synthetic YOLOv4-tiny weights) goes
+    through parse_cfg / load_weights into YoloEngine and must give the heads of the engine built directly from the
+    builder's layer list and weights (the only difference is one fp32 rounding of the identity BN scale)."""
+    from fastmot_b200.engine import YoloEngine
+    from fastmot_b200.models import darknet
+    layers = darknet.yolov4_tiny()
+    weights = darknet.synthetic_weights(layers, 3)
+    cfg_path, w_path = tmp_path / "net.cfg", tmp_path / "net.weights"
+    cfg_path.write_text(darknet.to_cfg(layers, 416, 416))
+    darknet.save_weights(str(w_path), layers, weights, 3)
+    net, layers2 = darknet.parse_cfg(cfg_path.read_text())
+    assert (net['width'], net['height']) == (416, 416) and len(layers2) == len(layers)
+    loaded = darknet.load_weights(str(w_path), layers2, 3)
+    assert sorted(loaded) == sorted(weights)
+    for i in weights:
+        np.testing.assert_allclose(loaded[i][0], weights[i][0], rtol=3e-7, atol=1e-9)
+        np.testing.assert_array_equal(loaded[i][1], np.asarray(weights[i][1], np.float32))
+    a = YoloEngine(layers, (416, 416), weights, use_graph=False)
+    b = YoloEngine(layers2, (416, 416), loaded, use_graph=False)
+    x = torch.rand(416, 416, 8, device="cuda").half()
+    x[..., 3:] = 0
+    ha = [h.clone().float() for h in a.forward(x)]
+    hb = [h.float() for h in b.forward(x)]
+    assert len(ha) == len(hb) == 2
+    for p, q in zip(ha, hb):
+        assert p.shape == q.shape
+        assert float((p - q).abs().max()) <= 2e-3 * float(p.abs().max() + 1)

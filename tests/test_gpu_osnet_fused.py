@@ -233,7 +233,7 @@ def test_osnet_stem_vs_torch(n):
     """Fused 7x7/2 conv + ReLU + 3x3/2 max-pool (TMA 5-D window tiles) against fp32 torch."""
     from fastmot_b200 import _lib
     from fastmot_b200.devmem import ptr, stream_ptr
-    from fastmot_b200.packing import pack_b_sw128
+    from fastmot_b200.packing import pack_b_sw64
     lib = _lib.require_device()
     rng = np.random.default_rng(7)
     w7 = rng.normal(0, np.sqrt(2.0 / 147), (64, 7, 7, 3)).astype(np.float32)
@@ -242,9 +242,9 @@ def test_osnet_stem_vs_torch(n):
     x = torch.randn(n, 256, 128, 3, generator=g).half()
     xin = torch.zeros(n, 264, 136, 4, dtype=torch.float16)
     xin[:, 4:-4, 4:-4, :3] = x
-    wk = np.zeros((64, 8, 8, 4), np.float32)
-    wk[:, :7, 1:8, :3] = w7
-    img = torch.as_tensor(pack_b_sw128(wk.reshape(64, 256))).cuda()
+    wk = np.zeros((64, 7, 8, 4), np.float32)
+    wk[:, :, 1:8, :3] = w7
+    img = torch.as_tensor(pack_b_sw64(wk.reshape(64, 224))).cuda()
     out = torch.full((n, 64, 32, 64), float('nan'), dtype=torch.float16, device="cuda")
     xin_d, b_d = xin.cuda(), torch.as_tensor(b7).cuda()
     _lib.check(lib.fm_osnet_stem(ptr(xin_d), n, ptr(img), ptr(b_d), ptr(out), stream_ptr()), "fm_osnet_stem")
