@@ -100,6 +100,8 @@ SIGNATURES = {
     "fm_add_act_strided": (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_p, c_i, c_i, c_ll, c_i, c_i, c_p]),
     "fm_conv2d_tc": (c_i, [C.POINTER(FmConvDesc), c_p, c_p, c_p, c_p, c_p, c_p]),
     "fm_conv2d_tc_supported": (c_i, [C.POINTER(FmConvDesc)]),
+    "fm_conv2d_tma": (c_i, [C.POINTER(FmConvDesc), c_p, c_p, c_p, c_p, c_p, c_p]),
+    "fm_conv2d_tma_supported": (c_i, [C.POINTER(FmConvDesc)]),
     "fm_dwconv3": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "fm_global_avgpool": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p]),
     "fm_channel_gate": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),

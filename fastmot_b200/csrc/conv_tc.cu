@@ -23,6 +23,7 @@
 // PTX ISA "tcgen05 matrix / instruction descriptor" tables (cross-checked against cute/arch/mma_sm100_desc.hpp).
 #include "common.cuh"
 #include "../../include/fastmot_b200.h"
+#include "conv_act.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -107,51 +108,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ float tc_mish(float v) {
-    // x * tanh(softplus(x)) with n = e^x:  tanh(log(1+n)) = n(n+2) / (n(n+2) + 2)  -- one ex2, one rcp, no cancellation
-    const float n = __expf(fminf(v, 20.f));
-    const float t = n * (n + 2.f);
-    return v > 20.f ? v : v * __fdividef(t, t + 2.f);
-}
-
-__device__ __forceinline__ float tc_act(float v, int act) {
-    switch (act) {
-        case FM_ACT_LEAKY: return v > 0.f ? v : 0.1f * v;
-        case FM_ACT_RELU: return fmaxf(v, 0.f);
-        case FM_ACT_MISH: return tc_mish(v);
-        case FM_ACT_SWISH: return __fdividef(v, 1.f + __expf(-v));
-        case FM_ACT_LOGISTIC: return __fdividef(1.f, 1.f + __expf(-v));
-        default: return v;
-    }
-}
-
-// activation of 8 values with the (warp-uniform) switch hoisted out of the element loop
-__device__ __forceinline__ void tc_act8(float (&v)[8], int act) {
-    switch (act) {
-        case FM_ACT_LEAKY:
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = v[q] > 0.f ? v[q] : 0.1f * v[q];
-            break;
-        case FM_ACT_RELU:
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
-            break;
-        case FM_ACT_MISH:
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = tc_mish(v[q]);
-            break;
-        case FM_ACT_SWISH:
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = __fdividef(v[q], 1.f + __expf(-v[q]));
-            break;
-        case FM_ACT_LOGISTIC:
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = __fdividef(1.f, 1.f + __expf(-v[q]));
-            break;
-        default: break;
-    }
 }
 
 __device__ unsigned long long* g_dbg_dev = nullptr;   // optional per-CTA phase timestamps (scripts/bench_conv.py)

@@ -56,7 +56,8 @@ class _Net:
         self.launches = []
         self._graph = None
         self._keep = []
-        self.n_tc = self.n_simt = 0
+        self.n_tc = self.n_simt = self.n_tma = 0
+        self.use_tma = os.environ.get("FM_CONV_TMA", "1") != "0"     # A/B switch: 0 = every conv through conv_tc.cu
         self.layer_bytes = 0        # algorithmic HBM bytes of the conv / depthwise layers (each tensor moved once)
         self.dev = torch.device("cuda")
         # split-K scratch of the tcgen05 conv: one per engine, so engines on different streams never share partials
@@ -68,7 +69,11 @@ class _Net:
         self._keep.append(desc)
         self.layer_bytes += 2 * (desc.n * desc.hi * desc.wi * desc.cin + desc.n * desc.ho * desc.wo * desc.cout
                                  * (2 if residual is not None else 1) + desc.kh * desc.kw * desc.cin * desc.cout)
-        if self.use_tc and lib.fm_conv2d_tc_supported(C.byref(desc)):
+        if self.use_tc and self.use_tma and lib.fm_conv2d_tma_supported(C.byref(desc)):
+            fn = lib.fm_conv2d_tma          # TMA-fed, cluster split-K (csrc/conv_tma.cu)
+            self.n_tc += 1
+            self.n_tma += 1
+        elif self.use_tc and lib.fm_conv2d_tc_supported(C.byref(desc)):
             fn = lib.fm_conv2d_tc
             self.n_tc += 1
         else:
@@ -146,13 +151,30 @@ class YoloEngine(_Net):
         self.views = []     # per layer: (tensor, c, c_stride, c_off, h, w)
         self.params = {}
         self.heads = []
+        # shortcut layers (yolo2onnx.py:707-731) whose first operand is the convolution right before them and is read
+        # by nothing else: the add moves into that conv's epilogue (residual after the activation), one launch less
+        refs = {}
+        for i, l in enumerate(L):
+            if l['type'] == 'route':
+                for s_ in l['layers_abs']:
+                    refs.setdefault(s_, set()).add(i)
+            elif l['type'] == 'shortcut':
+                refs.setdefault(l['from_abs'], set()).add(i)
+        fuse_sc = os.environ.get("FM_FUSE_SHORTCUT", "1") != "0"
+        self.fused_shortcuts = set()
+        for i, l in enumerate(L[:-1]):
+            nx = L[i + 1]
+            if fuse_sc and l['type'] == 'convolutional' and nx['type'] == 'shortcut' and i not in home and \
+                    nx.get('activation', 'linear') == 'linear' and not refs.get(i) and nx['from_abs'] < i and \
+                    self.shapes[nx['from_abs']] == self.shapes[i]:
+                self.fused_shortcuts.add(i + 1)
         for i, l in enumerate(L):
             t = l['type']
             c, h, w = self.shapes[i]
             if i in home:
                 ri, off = home[i]
                 out = (route_buf(ri), c, self.shapes[ri][0], off, h, w)
-            elif t in ('convolutional', 'maxpool', 'upsample', 'shortcut'):
+            elif t in ('convolutional', 'maxpool', 'upsample', 'shortcut') and i not in self.fused_shortcuts:
                 out = (torch.zeros(h, w, c, dtype=torch.float16, device=self.dev), c, c, 0, h, w)
             else:
                 out = None
@@ -169,13 +191,20 @@ class YoloEngine(_Net):
                 pad = k // 2 if l.get('pad', 0) else 0
                 d = _conv_desc(1, src[4], src[5], cin, src[2], src[3], h, w, c, out[2], out[3], k, l.get('stride', 1),
                                pad, _ACT[l.get('activation', 'linear')])
-                self._conv(d, src[0], wd, bd, out[0])
+                if i + 1 in self.fused_shortcuts:
+                    b = self.views[L[i + 1]['from_abs']]
+                    d.res_stride, d.res_offset = b[2], b[3]
+                    self._conv(d, src[0], wd, bd, out[0], residual=b[0])
+                else:
+                    self._conv(d, src[0], wd, bd, out[0])
             elif t == 'maxpool':
                 self._add('fm_maxpool', ptr(src[0]), ptr(out[0]), 1, src[4], src[5], src[1], src[2], src[3],
                           l['size'], l['stride'], out[2], out[3])
             elif t == 'upsample':
                 self._add('fm_upsample_copy', ptr(src[0]), ptr(out[0]), 1, src[4], src[5], src[1], src[2], src[3],
                           l['stride'], out[2], out[3])
+            elif t == 'shortcut' and i in self.fused_shortcuts:
+                out = self.views[i - 1]          # already holds conv + residual
             elif t == 'shortcut':
                 a, b = self.views[i - 1], self.views[l['from_abs']]
                 self._add('fm_add_act_strided', ptr(a[0]), a[2], a[3], ptr(b[0]), b[2], b[3], ptr(out[0]), out[2],

@@ -201,6 +201,13 @@ int fm_conv2d_simt(const FmConvDesc* h_desc, const void* in, const void* wgt, co
 int fm_conv2d_tc(const FmConvDesc* h_desc, const void* in, const void* wgt, const float* bias, const void* residual,
                  void* out, void* stream);
 int fm_conv2d_tc_supported(const FmConvDesc* h_desc);
+/* Warp-specialised TMA + tcgen05 path with the split-K reduction inside a thread-block cluster (csrc/conv_tma.cu):
+ * 1x1 / 3x3, stride 1, "same" padding, cin % 64 == 0, 8-channel aligned views; batch 1 for 3x3.  Needs no workspace
+ * (FmConvDesc.ws is ignored).  Same role as fm_conv2d_tc: the TensorRT conv tactics behind
+ * fastmot/utils/inference.py:106-117. */
+int fm_conv2d_tma(const FmConvDesc* h_desc, const void* in, const void* wgt, const float* bias, const void* residual,
+                  void* out, void* stream);
+int fm_conv2d_tma_supported(const FmConvDesc* h_desc);
 /* Darknet maxpool (SAME_UPPER, yolo2onnx.py:838-863) with channel-slice in/out; PyTorch-style padded maxpool. */
 int fm_maxpool(const void* in, void* out, int n, int hi, int wi, int c, int cin_stride, int cin_off, int k, int stride,
                int cout_stride, int cout_off, void* stream);

@@ -50,6 +50,8 @@ def _run_conv(fn_name, case, seed=0):
         d.res_stride, d.res_offset = cout, 0
     if fn_name == 'fm_conv2d_tc' and not lib.fm_conv2d_tc_supported(C.byref(d)):
         return None
+    if fn_name == 'fm_conv2d_tma':
+        assert lib.fm_conv2d_tma_supported(C.byref(d)), case
     xd, wd, bd, od = xin.cuda(), wt.cuda(), bias.cuda(), out.cuda()
     rd = res.cuda() if use_res else None
     rc = getattr(lib, fn_name)(C.byref(d), ptr(xd), ptr(wd), ptr(bd), ptr(rd), ptr(od), stream_ptr())
@@ -92,6 +94,47 @@ def test_conv_tc_vs_torch(case):
     r = _run_conv('fm_conv2d_tc', case)
     if r is None:
         pytest.skip("shape not handled by the tcgen05 path (falls back to the SIMT kernel)")
+
+
+TMA_CASES = [
+    # n, h, w, cin, cout, k, stride, act, cin_stride, cin_off, cout_stride, cout_off, residual
+    (1, 80, 80, 128, 128, 3, 1, 'mish', 128, 0, 128, 0, False),       # 16x8 rectangles, cluster of 8 (18 K slices)
+    (1, 80, 80, 128, 128, 3, 1, 'mish', 128, 0, 128, 0, True),        # fused CSP shortcut
+    (1, 80, 80, 256, 128, 1, 1, 'mish', 256, 0, 256, 128, False),     # 1x1 into a concat slice, 2-way split
+    (1, 80, 80, 128, 256, 3, 1, 'leaky', 128, 0, 256, 0, False),      # 100 tiles: no split
+    (1, 40, 40, 256, 256, 3, 1, 'mish', 256, 0, 256, 0, True),        # 40x3 rectangles (120 rows used), split 8
+    (1, 40, 40, 512, 256, 1, 1, 'mish', 512, 0, 256, 0, False),       # 64-wide filter tiles, split 4
+    (1, 40, 40, 256, 512, 3, 1, 'leaky', 256, 0, 512, 0, False),
+    (1, 20, 20, 512, 512, 3, 1, 'mish', 512, 0, 512, 0, False),       # 20x6 rectangles, 72 K slices
+    (1, 20, 20, 1024, 512, 1, 1, 'mish', 2048, 1024, 512, 0, False),  # input channel slice of a concat buffer
+    (1, 20, 20, 2048, 512, 1, 1, 'leaky', 2048, 0, 512, 0, False),    # SPP output: 32 K slices
+    (1, 20, 20, 512, 1024, 3, 1, 'mish', 512, 0, 1024, 0, False),
+    (1, 13, 13, 512, 256, 1, 1, 'leaky', 1024, 512, 256, 0, False),   # ragged last tile (169 pixels)
+    (1, 19, 23, 64, 64, 3, 1, 'relu', 64, 0, 64, 0, True),            # odd plane, single K chunk per tap
+    (1, 26, 26, 256, 40, 1, 1, 'logistic', 256, 0, 40, 0, False),     # cout < filter tile (rows beyond cout masked)
+    (3, 16, 8, 192, 384, 1, 1, 'linear', 192, 0, 384, 0, True),       # batch > 1 (flattened 1x1), 3 K slices
+    (40, 64, 32, 256, 256, 1, 1, 'relu', 256, 0, 256, 0, False),      # OSNet transition geometry: 640 tiles, no split
+    (1, 160, 160, 64, 64, 3, 1, 'mish', 64, 0, 128, 64, False),       # 200 tiles, concat slice
+    (1, 6, 5, 64, 32, 3, 1, 'linear', 64, 0, 32, 0, False),           # plane smaller than one tile
+]
+
+
+@pytest.mark.parametrize("case", TMA_CASES)
+def test_conv_tma_vs_torch(case):
+    """TMA-fed tcgen05 conv with in-cluster split-K (csrc/conv_tma.cu) vs fp32 torch."""
+    assert _run_conv('fm_conv2d_tma', case)
+
+
+@pytest.mark.parametrize("split", ["1", "2", "5", "8"])
+def test_conv_tma_split_sizes_agree(split, monkeypatch):
+    """Every cluster size gives the same layer (fp32 partial sums; order of summation differs -> tolerance)."""
+    import subprocess, sys, os
+    code = ("import sys; sys.path.insert(0, 'tests'); import test_gpu_nets as t; "
+            "[t._run_conv('fm_conv2d_tma', c) for c in (t.TMA_CASES[4], t.TMA_CASES[7], t.TMA_CASES[9])]")
+    env = dict(os.environ, FM_CONV_TMA_SPLIT=split)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
 
 
 def _yolo_vs_oracle(name, hw, tol):
@@ -177,6 +220,11 @@ def test_deep_yolo_engine_layerwise(name, hw):
             k = l['size']
             want = _act(F.conv2d(src, torch.as_tensor(w).half().float().permute(0, 3, 1, 2), torch.as_tensor(b),
                                  stride=l.get('stride', 1), padding=k // 2), l.get('activation', 'linear'))
+            if i + 1 in eng.fused_shortcuts:      # the shortcut's add runs in this conv's epilogue
+                want = want + fetch(eng.layers[i + 1]['from_abs'])
+        elif t == 'shortcut' and i in eng.fused_shortcuts:
+            assert eng.views[i][0].data_ptr() == eng.views[i - 1][0].data_ptr()
+            continue
         elif t == 'maxpool':
             want = _same_upper_pool(src, l['size'], l['stride'])
         elif t == 'upsample':
