@@ -6,9 +6,11 @@
 
 static __device__ __forceinline__ float tc_mish(float v) {
     // x * tanh(softplus(x)) with n = e^x:  tanh(log(1+n)) = n(n+2) / (n(n+2) + 2)  -- one ex2, one rcp, no cancellation
+    // branch-free: for v >= 20 the clamp gives t = e^20 (e^20 + 2) ~ 2.4e17 and t / (t + 2) rounds to 1.0f, i.e. v.
+    // (A `v > 20 ? v : ...` select compiled to a divergent branch per element: eight serial MUFU chains per pixel row.)
     const float n = __expf(fminf(v, 20.f));
     const float t = n * (n + 2.f);
-    return v > 20.f ? v : v * __fdividef(t, t + 2.f);
+    return v * __fdividef(t, t + 2.f);
 }
 
 static __device__ __forceinline__ float tc_act(float v, int act) {

@@ -24,15 +24,6 @@ constexpr int STEM_NS = 6;             // TMA ring depth (8 KB stages, one kerne
 constexpr int STEM_KR = 7;             // kernel rows
 constexpr int STEM_ROWP = 64 * 128 + 64 * 16;   // one conv row: 64 px x (128 B + 16 B pad)
 
-__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
-        "r"(c3), "r"(c4)
-        : "memory");
-}
-
 __device__ float* g_stem_dbg = nullptr;        // debugging aid (scripts/debug_stem.py): raw accumulators + A slices of CTA 0, tile 0
 
 struct StemArgs {

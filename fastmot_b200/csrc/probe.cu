@@ -40,6 +40,27 @@ int fm_make_tmap_f16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_
     return FM_OK;
 }
 
+int fm_make_tmap_f16_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                        const uint32_t* box) {
+    fm_encode_tiled_fn enc = fm_get_encode_tiled();
+    if (!enc) { fm_set_last_error("cuTensorMapEncodeTiled not available"); return FM_ERR_CUDA; }
+    if (rank < 1 || rank > 5) { fm_set_last_error("fm_make_tmap_f16_nd: rank"); return FM_ERR_ARG; }
+    cuuint64_t d[5], st[4];
+    cuuint32_t bx[5], estr[5] = {1, 1, 1, 1, 1};
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; }
+    for (int i = 0; i + 1 < rank; ++i) st[i] = strides[i] * 2;      // bytes
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, st, bx, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[128];
+        snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled (rank %d) failed (%d)", rank, (int)r);
+        fm_set_last_error(buf);
+        return FM_ERR_CUDA;
+    }
+    return FM_OK;
+}
+
 namespace {
 
 __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUtensorMap map_a, int row0,

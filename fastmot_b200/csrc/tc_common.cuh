@@ -62,6 +62,20 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
         "r"(c3)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3), "r"(c4)
+        : "memory");
+}
+// L2 prefetch of one box (no shared memory, no barrier): warms the cache ahead of the real load
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -193,3 +207,6 @@ fm_encode_tiled_fn fm_get_encode_tiled();
 // fp16 tensor [d2][d1][d0] (d0 contiguous, strides in elements), box (b0, b1, b2), 128-byte swizzle, zero OOB fill
 int fm_make_tmap_f16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
                         uint64_t stride2, uint32_t b0, uint32_t b1, uint32_t b2);
+// general form: rank <= 5, dims / box fastest dimension first, strides (elements) of dims 1..rank-1
+int fm_make_tmap_f16_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                        const uint32_t* box);

@@ -168,6 +168,7 @@ class YoloEngine(_Net):
                     nx.get('activation', 'linear') == 'linear' and not refs.get(i) and nx['from_abs'] < i and \
                     self.shapes[nx['from_abs']] == self.shapes[i]:
                 self.fused_shortcuts.add(i + 1)
+        spp_prev = {}
         for i, l in enumerate(L):
             t = l['type']
             c, h, w = self.shapes[i]
@@ -198,8 +199,17 @@ class YoloEngine(_Net):
                 else:
                     self._conv(d, src[0], wd, bd, out[0])
             elif t == 'maxpool':
-                self._add('fm_maxpool', ptr(src[0]), ptr(out[0]), 1, src[4], src[5], src[1], src[2], src[3],
-                          l['size'], l['stride'], out[2], out[3])
+                ksz, psrc = l['size'], src
+                key = (src[0].data_ptr(), src[1], src[2], src[3])
+                if l['stride'] == 1 and ksz % 2 == 1:
+                    # SPP (5 / 9 / 13 on the same tensor): a k x k stride-1 max over a k0 x k0 max is the
+                    # (k + k0 - 1) window, so 9 = 5 o 5 and 13 = 5 o 9 -- each pool reads 25 taps instead of 81 / 169
+                    prev = spp_prev.get(key)
+                    if prev is not None and ksz > prev[0]:
+                        ksz, psrc = ksz - prev[0] + 1, prev[1]
+                    spp_prev[key] = (l['size'], out)
+                self._add('fm_maxpool', ptr(psrc[0]), ptr(out[0]), 1, psrc[4], psrc[5], psrc[1], psrc[2], psrc[3],
+                          ksz, l['stride'], out[2], out[3])
             elif t == 'upsample':
                 self._add('fm_upsample_copy', ptr(src[0]), ptr(out[0]), 1, src[4], src[5], src[1], src[2], src[3],
                           l['stride'], out[2], out[3])

@@ -116,6 +116,12 @@ TMA_CASES = [
     (40, 64, 32, 256, 256, 1, 1, 'relu', 256, 0, 256, 0, False),      # OSNet transition geometry: 640 tiles, no split
     (1, 160, 160, 64, 64, 3, 1, 'mish', 64, 0, 128, 64, False),       # 200 tiles, concat slice
     (1, 6, 5, 64, 32, 3, 1, 'linear', 64, 0, 32, 0, False),           # plane smaller than one tile
+    (1, 80, 80, 128, 256, 3, 2, 'mish', 128, 0, 256, 0, False),       # stride 2 through the 5-D parity view
+    (1, 40, 40, 256, 512, 3, 2, 'leaky', 256, 0, 512, 0, False),      # stride 2, 36 K slices, split
+    (1, 320, 320, 64, 128, 3, 2, 'mish', 64, 0, 128, 0, False),       # stride 2, 200 tiles
+    (1, 26, 22, 64, 64, 3, 2, 'relu', 128, 64, 64, 0, False),         # stride 2, channel slice in, ragged tiles
+    (1, 40, 40, 512, 18, 1, 1, 'logistic', 512, 0, 18, 0, False),     # detection head: 18 channels, element-wise stores
+    (1, 20, 20, 1024, 18, 1, 1, 'linear', 1024, 0, 18, 0, False),     # head with a deep K split
 ]
 
 
