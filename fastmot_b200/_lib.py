@@ -50,6 +50,12 @@ class FmOsbMerge(C.Structure):
                 ("wimg", c_p), ("bias", c_p), ("x", c_p), ("res", c_p), ("out", c_p), ("gate_scratch", c_p)]
 
 
+class FmCascadeDesc(C.Structure):
+    _fields_ = [(k, c_i) for k in ("n_det", "n_conf", "n_groups", "n_unconf", "n_hist", "cap")] + \
+               [(k, c_p) for k in ("goff", "conf_active", "feat_cost", "iou_cost", "reid_cost", "det_conf",
+                                   "det_occluded", "sub", "out")] + [("conf_thresh", c_d), ("max_reid_cost", c_d)]
+
+
 class FmYoloHead(C.Structure):
     _fields_ = [("anchors", c_f * 12), ("scale_x_y", c_f)]
 
@@ -74,6 +80,8 @@ SIGNATURES = {
     "fm_lsa_workspace_bytes": (c_ll, [c_i, c_i]),
     "fm_lsa": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_p]),
     "fm_greedy_match": (c_i, [c_p, c_i, c_i, c_d, c_p, c_p, c_p]),
+    "fm_assoc_cascade": (c_i, [C.POINTER(FmCascadeDesc), c_p]),
+    "fm_assoc_cascade_out_ints": (c_ll, [c_i]),
     "fm_letterbox_preproc": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "fm_roi_resize_norm": (c_i, [c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
     "fm_yolo_decode_filter": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, C.POINTER(FmYoloHead), c_i, c_i, c_i, c_i, c_i, c_p,

@@ -338,6 +338,84 @@ __global__ void __launch_bounds__(256) fc_norm_warp_kernel(const float* __restri
     }
 }
 
+// Same op for the ReID head (200 x 512 -> 512, feature_extractor.py:62-74) spread over the whole GPU: a cluster of 8 CTAs
+// shares S samples, CTA r computes output features [r * cout / 8, (r + 1) * cout / 8) (a warp per feature, lanes along
+// the weight row), the per-sample sums of squares are exchanged through distributed shared memory and added in rank
+// order (deterministic), and every CTA normalises and stores its own slice.  The two-samples-per-CTA kernel above made
+// 100 CTAs each stream the whole 1 MB weight matrix (76 us); this one reads it 25 times with 200 CTAs.
+template <int S>
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(256)
+fc_norm_cluster_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                       float* __restrict__ out, int n, int cin, int cout, int relu, int normalize) {
+    extern __shared__ float fsm[];   // x[S][cin]
+    __shared__ float sy[S][128];     // this CTA's slice of the outputs (cout / 8 <= 128)
+    __shared__ float s_ssq[S], s_inv[S];
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int ob = cout >> 3, j0 = (int)rank * ob;
+    const int b0 = (int)(blockIdx.x >> 3) * S;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < S * cin; i += blockDim.x) {
+        const int s = i / cin, b = b0 + s;
+        fsm[i] = b < n ? in[(size_t)b * cin + (i - s * cin)] : 0.f;
+    }
+    __syncthreads();
+    const int c4 = cin >> 2;
+    for (int jj = warp; jj < ob; jj += 8) {
+        const float4* wr = reinterpret_cast<const float4*>(w + (size_t)(j0 + jj) * cin);
+        float acc[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) acc[s] = 0.f;
+        for (int i = lane; i < c4; i += 32) {
+            const float4 wv = __ldg(wr + i);
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                const float4 xv = reinterpret_cast<const float4*>(fsm + (size_t)s * cin)[i];
+                acc[s] += wv.x * xv.x + wv.y * xv.y + wv.z * xv.z + wv.w * xv.w;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            float a = warp_sum(acc[s]);
+            if (lane == 0) {
+                a += bias ? bias[j0 + jj] : 0.f;
+                if (relu) a = fmaxf(a, 0.f);
+                sy[s][jj] = a;
+            }
+        }
+    }
+    __syncthreads();
+    if (warp < S) {
+        float sq = 0.f;
+        for (int jj = lane; jj < ob; jj += 32) { const float a = sy[warp][jj]; sq += a * a; }
+        sq = warp_sum(sq);
+        if (lane == 0) s_ssq[warp] = sq;
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (threadIdx.x < S) {
+        float tot = 0.f;
+        const uint32_t laddr = (uint32_t)__cvta_generic_to_shared(&s_ssq[threadIdx.x]);
+#pragma unroll
+        for (uint32_t r = 0; r < 8; ++r) {
+            uint32_t raddr;
+            float v;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(r));
+            asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(raddr));
+            tot += v;
+        }
+        s_inv[threadIdx.x] = normalize ? 1.f / sqrtf(tot) : 1.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < S * ob; i += blockDim.x) {
+        const int s = i / ob, jj = i - s * ob, b = b0 + s;
+        if (b < n) out[(size_t)b * cout + j0 + jj] = sy[s][jj] * s_inv[s];
+    }
+    // nobody leaves while a peer may still read its sums
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // strided variant: operands are channel slices of wider NHWC buffers
 __global__ void add_act_strided_kernel(const __half* __restrict__ a, int a_stride, int a_off,
                                        const __half* __restrict__ b, int b_stride, int b_off, __half* __restrict__ out,
@@ -476,6 +554,19 @@ extern "C" int fm_channel_gate(const void* x, float* pooled, float* gate, const 
 extern "C" int fm_fc_norm(const float* in, const float* w, const float* bias, float* out, int n, int cin, int cout,
                           int relu, int normalize, void* stream) {
     if (n <= 0) return FM_OK;
+    if ((cin & 3) == 0 && cin <= 2048 && (cout & 7) == 0 && cout <= 1024 && n >= 16) {
+        constexpr int S = 8;
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(fc_norm_cluster_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, S * 2048 * 4);
+            attr = true;
+        }
+        const size_t smem = (size_t)S * cin * sizeof(float);
+        fc_norm_cluster_kernel<S><<<8 * ((n + S - 1) / S), 256, smem, (cudaStream_t)stream>>>(in, w, bias, out, n, cin, cout,
+                                                                                            relu, normalize);
+        FM_CHECK_LAUNCH("fm_fc_norm");
+        return FM_OK;
+    }
     if ((cin & 3) == 0 && cin <= 4096 && cout <= 4096) {
         constexpr int S = 2;
         const size_t smem = (size_t)S * (cin + cout) * sizeof(float);

@@ -274,6 +274,10 @@ class OSNetEngine(_Net):
     def __init__(self, width, weights=None, input_hw=(256, 128), feature_dim=512, max_batch=256, use_tc=True,
                  use_graph=False):
         super().__init__(use_tc, use_graph)
+        # The ReID stack's stand-alone convs are thousands of tiles with 1-8 K slices each: the one-tile-per-CTA TMA
+        # kernel pays its per-CTA set-up 20 times per SM there (OSNet x1.0 @200 crops: 2.89 ms with it, 2.66 ms with
+        # the cp.async kernel, profiles/r02_summary.md); it is the batch-1 detector layers it was written for.
+        self.use_tma = os.environ.get("FM_OSNET_TMA", "0") == "1"
         self.ops = osnet.build_osnet(width, feature_dim)
         self.weights = weights if weights is not None else osnet.synthetic_weights(self.ops)
         self.max_batch = max_batch

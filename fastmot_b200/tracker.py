@@ -8,8 +8,10 @@ of kernel launches and one D2H block (`Downlink`).
 """
 from types import SimpleNamespace
 from collections import OrderedDict
+import ctypes as C
 import itertools
 import logging
+import os
 
 import numpy as np
 import torch
@@ -114,6 +116,9 @@ class MultiTracker:
         self._homography_dev = torch.zeros(9, dtype=torch.float64, device=dev)
         self._h_ok_dev = torch.zeros(1, dtype=torch.int32, device=dev)
 
+        # FM_FUSE_CASCADE=0: one cost + assignment launch and one D2H per cascade stage (the r01 path, also taken for
+        # frames with more than 256 detections / tracks per list and for single-stage frames); 2: fused whenever it fits
+        self.fuse_cascade = {"0": 0, "2": 2}.get(os.environ.get("FM_FUSE_CASCADE", "1"), 1)   # 2 = always
         self._klt_bboxes = {}
         self._klt_stale = False
         self._klt_order = None
@@ -403,38 +408,50 @@ class MultiTracker:
         occ_fetched = False
 
         confirmed_by_depth, unconfirmed = self._group_tracks_by_depth()
-
-        # 1st association: appearance + motion, young tracks first
-        matches1 = []
-        u_trk_ids1 = []
-        u_det_ids = list(range(n_det))
-        for depth, trk_ids in enumerate(confirmed_by_depth):
-            if len(u_det_ids) == 0:
-                u_trk_ids1.extend(itertools.chain.from_iterable(confirmed_by_depth[depth:]))
-                break
-            if len(trk_ids) == 0:
-                continue
-            matches, u_trk_ids, u_det_ids = self._solve('feat', trk_ids, u_det_ids, ctx)
-            matches1 += matches
-            u_trk_ids1 += u_trk_ids
-
-        # 2nd association: IoU with still-active tracks
-        active = [trk_id for trk_id in u_trk_ids1 if self.tracks[trk_id].active]
-        u_trk_ids1 = [trk_id for trk_id in u_trk_ids1 if not self.tracks[trk_id].active]
-        matches2, u_trk_ids2, u_det_ids = self._solve('iou', active, u_det_ids, ctx)
-
-        # 3rd association: unconfirmed tracks
-        matches3, u_trk_ids3, u_det_ids = self._solve('iou', unconfirmed, u_det_ids, ctx)
-
-        # re-identification against the lost-track history
         hist_ids = [trk_id for trk_id, track in self.hist_tracks.items() if track.avg_feat.count >= 2]
-        if n_det:
-            occluded_det_mask = occ_dev[:n_det].cpu().numpy().astype(bool)
-        u_det_ids = [det_id for det_id in u_det_ids if det_conf[det_id] >= self.conf_thresh]
-        valid_u_det_ids = [det_id for det_id in u_det_ids if not occluded_det_mask[det_id]]
-        invalid_u_det_ids = [det_id for det_id in u_det_ids if occluded_det_mask[det_id]]
-        reid_matches, _, reid_u_det_ids = self._solve('reid', hist_ids, valid_u_det_ids, ctx, hist=True,
-                                                      greedy_max=self.max_reid_cost)
+
+        fused = None
+        # stages that will certainly run (the IoU stage of the still-active leftovers is only known on the device)
+        n_stages = sum(1 for g in confirmed_by_depth if g) + bool(unconfirmed) + bool(hist_ids)
+        if (self.fuse_cascade == 2 or (self.fuse_cascade and n_stages >= 2)) and 0 < n_det <= 256 and \
+                len(unconfirmed) <= 256 and len(hist_ids) <= 256 and sum(len(g) for g in confirmed_by_depth) <= 256:
+            # every stage in one launch, one D2H (csrc/assoc_cascade.cu).  With a single stage the per-stage path is
+            # already one launch pair + one D2H and skips the full IoU / re-id matrices, so it stays.
+            fused = self._cascade_fused(ctx, n_det, det_conf, confirmed_by_depth, unconfirmed, hist_ids, occ_dev)
+        if fused is not None:
+            (matches1, u_trk_ids1, matches2, u_trk_ids2, matches3, u_trk_ids3, reid_matches, invalid_u_det_ids,
+             reid_u_det_ids, occluded_det_mask) = fused
+        else:
+            # 1st association: appearance + motion, young tracks first
+            matches1 = []
+            u_trk_ids1 = []
+            u_det_ids = list(range(n_det))
+            for depth, trk_ids in enumerate(confirmed_by_depth):
+                if len(u_det_ids) == 0:
+                    u_trk_ids1.extend(itertools.chain.from_iterable(confirmed_by_depth[depth:]))
+                    break
+                if len(trk_ids) == 0:
+                    continue
+                matches, u_trk_ids, u_det_ids = self._solve('feat', trk_ids, u_det_ids, ctx)
+                matches1 += matches
+                u_trk_ids1 += u_trk_ids
+
+            # 2nd association: IoU with still-active tracks
+            active = [trk_id for trk_id in u_trk_ids1 if self.tracks[trk_id].active]
+            u_trk_ids1 = [trk_id for trk_id in u_trk_ids1 if not self.tracks[trk_id].active]
+            matches2, u_trk_ids2, u_det_ids = self._solve('iou', active, u_det_ids, ctx)
+
+            # 3rd association: unconfirmed tracks
+            matches3, u_trk_ids3, u_det_ids = self._solve('iou', unconfirmed, u_det_ids, ctx)
+
+            # re-identification against the lost-track history
+            if n_det:
+                occluded_det_mask = occ_dev[:n_det].cpu().numpy().astype(bool)
+            u_det_ids = [det_id for det_id in u_det_ids if det_conf[det_id] >= self.conf_thresh]
+            valid_u_det_ids = [det_id for det_id in u_det_ids if not occluded_det_mask[det_id]]
+            invalid_u_det_ids = [det_id for det_id in u_det_ids if occluded_det_mask[det_id]]
+            reid_matches, _, reid_u_det_ids = self._solve('reid', hist_ids, valid_u_det_ids, ctx, hist=True,
+                                                          greedy_max=self.max_reid_cost)
 
         matches = itertools.chain(matches1, matches2, matches3)
         u_trk_ids = itertools.chain(u_trk_ids1, u_trk_ids2, u_trk_ids3)
@@ -518,6 +535,91 @@ class MultiTracker:
         # start new tracks (tracker.py:287-293)
         new_det_ids = list(itertools.chain(invalid_u_det_ids, reid_u_det_ids))
         self._new_tracks(frame_id, det_tlbr, det_label, new_det_ids, p_tlbr)
+
+    def _cascade_fused(self, ctx, n_det, det_conf, confirmed_by_depth, unconfirmed, hist_ids, occ_dev):
+        """tracker.py:199-233 as three cost launches over ALL rows x ALL detections + one fm_assoc_cascade launch + one
+        D2H.  Returns the lists `update` continues with (same contents and orders as the per-stage path)."""
+        lib = self._lib
+        conf_ids = list(itertools.chain.from_iterable(confirmed_by_depth))
+        n_conf, n_unconf, n_hist = len(conf_ids), len(unconfirmed), len(hist_ids)
+        row_ids = conf_ids + list(unconfirmed)
+        n_rows = n_conf + n_unconf
+        if n_rows + n_hist == 0:
+            return None
+        goff = np.zeros(len(confirmed_by_depth) + 1, np.int32)
+        goff[1:] = np.cumsum([len(g) for g in confirmed_by_depth])
+        trks = [self.tracks[t] for t in row_ids]
+        slots = np.fromiter((t.slot for t in trks), np.int32, n_rows)
+        labels = np.fromiter((t.label for t in trks), np.int64, n_rows)
+        active = np.fromiter((t.active for t in trks[:n_conf]), np.uint8, n_conf)
+        h_slots = np.fromiter((self.hist_tracks[t].slot for t in hist_ids), np.int32, n_hist)
+        # reference quirk (tracker.py:364): labels are taken from the FIRST n_hist history tracks
+        h_labels = np.fromiter(itertools.islice((t.label for t in self.hist_tracks.values()), n_hist), np.int64, n_hist)
+        up = self.up
+        p_slots, p_labels, p_goff = up.put(slots), up.put(labels), up.put(goff)
+        p_active = up.put(active)
+        p_hslots, p_hlabels = up.put(h_slots), up.put(h_labels)
+        p_conf = up.put(np.ascontiguousarray(det_conf, np.float64))
+        up.flush()
+        need = (n_conf + n_rows + n_hist) * n_det + 256 * 256
+        if need > self._cost.numel():
+            self._cost = torch.empty(need, dtype=torch.float64, device=self._cost.device)
+        base = self._cost.data_ptr()
+        p_feat = C.c_void_p(base)
+        p_iou = C.c_void_p(base + 8 * n_conf * n_det)
+        p_reid = C.c_void_p(base + 8 * (n_conf + n_rows) * n_det)
+        p_sub = C.c_void_p(base + 8 * (n_conf + n_rows + n_hist) * n_det)
+        s = stream_ptr()
+        if n_conf:
+            fill = min(self.max_assoc_cost + 0.1, 1.)
+            _lib.check(lib.fm_matching_cost(ptr(self.pool.feat_avg), ptr(self.pool.feat_valid), ptr(self.pool.mean),
+                                            ptr(self.pool.cov), p_slots, p_labels, n_conf, ctx['emb'], ctx['tlbr'],
+                                            ctx['labels'], ctx['occ'], None, n_det, ctx['dim'], self.metric, fill,
+                                            self.motion_weight, self.max_assoc_cost, self.kf.params, p_feat, s),
+                       "fm_matching_cost")
+        if n_rows:
+            _lib.check(lib.fm_iou_cost(ptr(self.pool.tlbr), p_slots, p_labels, n_rows, ctx['tlbr'], ctx['labels'], None,
+                                       n_det, 1. - self.iou_thresh, p_iou, s), "fm_iou_cost")
+        if n_hist:
+            _lib.check(lib.fm_matching_cost(ptr(self.pool.feat_avg), None, ptr(self.pool.mean), ptr(self.pool.cov),
+                                            p_hslots, p_hlabels, n_hist, ctx['emb'], ctx['tlbr'], ctx['labels'], None,
+                                            None, n_det, ctx['dim'], self.metric, 1.0, -1.0, -1.0, self.kf.params,
+                                            p_reid, s), "fm_matching_cost")
+        cap = max(n_rows, n_det, n_hist, 1)
+        n_out = int(lib.fm_assoc_cascade_out_ints(cap))
+        self.down.reset()
+        p_out, _ = self.down.alloc((n_out,), np.int32)
+        d = _lib.FmCascadeDesc()
+        d.n_det, d.n_conf, d.n_groups, d.n_unconf, d.n_hist, d.cap = n_det, n_conf, len(confirmed_by_depth), n_unconf, \
+            n_hist, cap
+        d.goff, d.conf_active = p_goff, p_active
+        d.feat_cost, d.iou_cost, d.reid_cost = p_feat, p_iou, p_reid
+        d.det_conf, d.det_occluded = p_conf, ptr(occ_dev)
+        d.sub, d.out = p_sub, p_out
+        d.conf_thresh, d.max_reid_cost = float(self.conf_thresh), float(self.max_reid_cost)
+        _lib.check(lib.fm_assoc_cascade(C.byref(d), s), "fm_assoc_cascade")
+        o = self.down.fetch()[0]
+        hdr = o[:16]
+        if int(hdr[0]) != 0:
+            raise ValueError('cost matrix is infeasible')
+        arr = [o[16 + k * cap: 16 + (k + 1) * cap] for k in range(14)]
+
+        def pairs(rows, dets, n, ids):
+            return [(ids[r], int(c)) for r, c in zip(rows[:n].tolist(), dets[:n].tolist())]
+
+        def rows_of(a, n):
+            return [row_ids[r] for r in a[:n].tolist()]
+
+        n_m1, n_m2, n_m3, n_u1, n_u2, n_u3, n_reid, n_inv, n_ru = (int(v) for v in hdr[1:10])
+        matches1 = pairs(arr[0], arr[1], n_m1, row_ids)
+        matches2 = pairs(arr[2], arr[3], n_m2, row_ids)
+        matches3 = pairs(arr[4], arr[5], n_m3, row_ids)
+        u1, u2, u3 = rows_of(arr[6], n_u1), rows_of(arr[7], n_u2), rows_of(arr[8], n_u3)
+        reid_matches = pairs(arr[9], arr[10], n_reid, hist_ids)
+        invalid = arr[11][:n_inv].tolist()
+        reid_u = arr[12][:n_ru].tolist()
+        occ = arr[13][:n_det].astype(bool)
+        return matches1, u1, matches2, u2, matches3, u3, reid_matches, invalid, reid_u, occ
 
     def _feature_update(self, p_slots, p_idx, p_cnt, n, ctx):
         rc = self._lib.fm_feature_update(ptr(self.pool.feat_sum), ptr(self.pool.feat_avg), ptr(self.pool.feat_last),

@@ -125,6 +125,35 @@ int fm_lsa(const double* cost, int nr, int nc, int* col4row, int* status, void* 
 int fm_greedy_match(const double* cost, int nr, int nc, double max_cost, int* col4row, int* match_order,
                     void* stream);
 
+/* The whole association cascade of MultiTracker.update (fastmot/tracker.py:185-247) in one launch, id lists on the
+ * device (csrc/assoc_cascade.cu).  The caller computes the three cost matrices once for ALL rows x ALL detections
+ * (fm_matching_cost / fm_iou_cost with identity selections; an entry depends only on its pair):
+ *   feat_cost [n_conf x n_det]             confirmed tracks, concatenated by age-depth group (goff[n_groups + 1])
+ *   iou_cost  [(n_conf + n_unconf) x n_det] the same rows followed by the unconfirmed tracks
+ *   reid_cost [n_hist x n_det]             lost-track history
+ * Stages: LSA per depth group -> LSA of the still-active leftovers on IoU -> LSA of the unconfirmed tracks on IoU ->
+ * greedy re-identification of the confident, non-occluded leftovers.  Unmatched lists follow the reference's Numba
+ * typed-set order (matching.py:57-70).  Every dimension <= 256.
+ * out (ints, fm_assoc_cascade_out_ints(cap) of them): hdr[16] = {status (1 = infeasible LSA), n_m1, n_m2, n_m3, n_u1
+ * (inactive leftovers of stage 1), n_u2, n_u3, n_reid, n_invalid, n_reid_u}, then arrays of `cap` ints each:
+ * m1_row, m1_det, m2_row, m2_det, m3_row, m3_det, u1, u2, u3, reid_row, reid_det, invalid_det, reid_u_det, occluded.
+ * Rows are indices into the concatenated (confirmed | unconfirmed) order / the history order. */
+typedef struct FmCascadeDesc {
+    int n_det, n_conf, n_groups, n_unconf, n_hist, cap;
+    const int* goff;
+    const unsigned char* conf_active;   /* [n_conf] Track.active */
+    const double* feat_cost;
+    const double* iou_cost;
+    const double* reid_cost;
+    const double* det_conf;             /* [n_det] */
+    const unsigned char* det_occluded;  /* [n_det] fm_find_occluded */
+    double* sub;                        /* scratch, >= 256 * 256 doubles */
+    int* out;
+    double conf_thresh, max_reid_cost;
+} FmCascadeDesc;
+int fm_assoc_cascade(const FmCascadeDesc* h_desc, void* stream);
+long long fm_assoc_cascade_out_ints(int cap);
+
 /* ---------------------------------------------------------------- detector pre/post-processing --------------- */
 #define FM_MAX_ANCHORS 6 /* fastmot/plugins/yolo_layer.h:11 */
 typedef struct FmYoloHead {

@@ -265,3 +265,103 @@ def test_feature_update_matches_reference_semantics(lib):
         np.testing.assert_allclose(host(s)[slot], hs[slot], atol=1e-6)
         np.testing.assert_allclose(host(a)[slot], ha[slot], atol=1e-6)
     assert host(v).tolist() == [1, 0, 1, 0, 1]
+
+
+def _cascade_emulated(F, I, R, goff, active, conf, occ, conf_thresh, max_reid):
+    """tracker.py:199-233 on given cost matrices with the oracle's SciPy / Numba replays (oracle/assoc.py)."""
+    from oracle import assoc
+    n_conf, n_det = F.shape[0], F.shape[1]
+    u_det = list(range(n_det))
+    m1, u1 = [], []
+    for g in range(len(goff) - 1):
+        rows = list(range(goff[g], goff[g + 1]))
+        if not rows:
+            continue
+        if not u_det:
+            u1 += rows
+            continue
+        m, ur, u_det = assoc.linear_assignment(F[np.ix_(rows, u_det)], rows, u_det)
+        m1 += m
+        u1 += ur
+    act = [r for r in u1 if active[r]]
+    u1 = [r for r in u1 if not active[r]]
+
+    def stage(rows, u_det):
+        if not rows or not u_det:
+            return [], list(rows), list(u_det)
+        return assoc.linear_assignment(I[np.ix_(rows, u_det)], rows, u_det)
+    m2, u2, u_det = stage(act, u_det)
+    m3, u3, u_det = stage(list(range(n_conf, I.shape[0])), u_det)
+    u_det = [d for d in u_det if conf[d] >= conf_thresh]
+    valid = [d for d in u_det if not occ[d]]
+    invalid = [d for d in u_det if occ[d]]
+    hist = list(range(R.shape[0]))
+    if hist and valid:
+        reid, _, reid_u = assoc.greedy_match(R[np.ix_(hist, valid)], hist, valid, max_reid)
+    else:
+        reid, reid_u = [], valid
+    return m1, u1, m2, u2, m3, u3, reid, invalid, reid_u
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_assoc_cascade_vs_per_stage_emulation(seed):
+    """fm_assoc_cascade (all stages in one launch, lists on the device) == the stage-by-stage cascade built from the
+    oracle's SciPy LSA replay, Numba set order and greedy match, on random cost matrices with INF gates, exact ties
+    (quantised costs), empty groups, occluded / low-confidence detections."""
+    import ctypes as C
+    from fastmot_b200 import _lib
+    from fastmot_b200.devmem import ptr, stream_ptr
+    from gpu_util import dev, host
+    lib = _lib.require_device()
+    rng = np.random.default_rng(100 + seed)
+    n_det = int(rng.integers(1, 200)) if seed else 200
+    sizes = [int(rng.integers(0, 90)) if rng.random() > 0.25 else 0 for _ in range(4)] if seed else [200, 0, 0, 0]
+    while sum(sizes) > 256:
+        sizes[int(np.argmax(sizes))] //= 2
+    goff = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    n_conf = int(goff[-1])
+    n_unconf = int(rng.integers(0, 40))
+    n_hist = int(rng.integers(0, 50))
+
+    def costs(nr, quant):
+        c = rng.uniform(0, 1, (nr, n_det))
+        if quant:
+            c = np.round(c * quant) / quant          # exact ties
+        c[rng.random((nr, n_det)) < 0.35] = 1e5       # gated pairs
+        return np.ascontiguousarray(c)
+    F = costs(n_conf, 16 if seed % 2 else 0)
+    I = costs(n_conf + n_unconf, 8 if seed % 3 == 0 else 0)
+    R = costs(n_hist, 0)
+    active = (rng.random(n_conf) < 0.6).astype(np.uint8)
+    conf = rng.uniform(0.3, 1.0, n_det)
+    occ = (rng.random(n_det) < 0.2).astype(np.uint8)
+    want = _cascade_emulated(F, I, R, goff, active, conf, occ, 0.5, 0.6)
+
+    cap = max(n_conf + n_unconf, n_det, n_hist, 1)
+    n_out = int(lib.fm_assoc_cascade_out_ints(cap))
+    keep = [dev(a) for a in (goff, active if n_conf else np.zeros(1, np.uint8), F.reshape(-1) if F.size else np.zeros(1),
+                             I.reshape(-1) if I.size else np.zeros(1), R.reshape(-1) if R.size else np.zeros(1), conf, occ)]
+    sub = torch.zeros(256 * 256, dtype=torch.float64, device="cuda")
+    out = torch.full((n_out,), -9, dtype=torch.int32, device="cuda")
+    d = _lib.FmCascadeDesc()
+    d.n_det, d.n_conf, d.n_groups, d.n_unconf, d.n_hist, d.cap = n_det, n_conf, 4, n_unconf, n_hist, cap
+    d.goff, d.conf_active, d.feat_cost, d.iou_cost, d.reid_cost, d.det_conf, d.det_occluded = (ptr(t) for t in keep)
+    d.sub, d.out = ptr(sub), ptr(out)
+    d.conf_thresh, d.max_reid_cost = 0.5, 0.6
+    _lib.check(lib.fm_assoc_cascade(C.byref(d), stream_ptr()), "fm_assoc_cascade")
+    o = host(out)
+    hdr = o[:16]
+    assert hdr[0] == 0
+    arr = [o[16 + k * cap: 16 + (k + 1) * cap] for k in range(14)]
+    n = [int(v) for v in hdr[1:10]]
+
+    def pairs(a, b, k):
+        return list(zip(a[:k].tolist(), b[:k].tolist()))
+    got = (pairs(arr[0], arr[1], n[0]), arr[6][:n[3]].tolist(), pairs(arr[2], arr[3], n[1]), arr[7][:n[4]].tolist(),
+           pairs(arr[4], arr[5], n[2]), arr[8][:n[5]].tolist(), pairs(arr[9], arr[10], n[6]), arr[11][:n[7]].tolist(),
+           arr[12][:n[8]].tolist())
+    names = ("matches1", "u_trk1", "matches2", "u_trk2", "matches3", "u_trk3", "reid", "invalid", "reid_u")
+    for nm, g_, w_ in zip(names, got, want):
+        assert [tuple(x) if isinstance(x, (tuple, list)) else x for x in g_] == \
+               [tuple(x) if isinstance(x, (tuple, list)) else x for x in w_], (seed, nm, g_, w_)
+    assert np.array_equal(arr[13][:n_det], occ)

@@ -256,3 +256,29 @@ def test_osnet_stem_vs_torch(n):
     assert torch.isfinite(got).all()
     err = float((got - want).abs().max()) / (float(want.abs().max()) + 1e-6)
     assert err < 3e-3, err
+
+
+@pytest.mark.parametrize("n,cin,cout,relu", [(200, 512, 512, 0), (37, 512, 512, 1), (16, 256, 128, 0), (6, 512, 512, 0)])
+def test_fc_norm_vs_torch(n, cin, cout, relu):
+    """ReID head: fc + L2 normalisation (feature_extractor.py:62-74): cluster kernel (n >= 16) and the small-batch kernel."""
+    import torch.nn.functional as F
+    from fastmot_b200 import _lib
+    from fastmot_b200.devmem import ptr, stream_ptr
+    lib = _lib.require_device()
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n, cin, generator=g)
+    w = torch.randn(cout, cin, generator=g) * 0.05
+    b = torch.randn(cout, generator=g) * 0.1
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    out = torch.zeros(n, cout, dtype=torch.float32, device="cuda")
+    _lib.check(lib.fm_fc_norm(ptr(xd), ptr(wd), ptr(bd), ptr(out), n, cin, cout, relu, 1, stream_ptr()), "fm_fc_norm")
+    torch.cuda.synchronize()
+    y = x @ w.t() + b
+    if relu:
+        y = y.clamp_min(0)
+    want = F.normalize(y, dim=1)
+    assert float((out.cpu() - want).abs().max()) < 2e-5
+    out2 = torch.zeros_like(out)
+    _lib.check(lib.fm_fc_norm(ptr(xd), ptr(wd), ptr(bd), ptr(out2), n, cin, cout, relu, 1, stream_ptr()), "fm_fc_norm")
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)          # deterministic (fixed summation order across the cluster)

@@ -72,3 +72,18 @@ def test_sequence_ids_and_boxes_exact(name):
         assert trk.tracks[int(k)].avg_feat.count == cnt
         if cnt:
             np.testing.assert_allclose(trk.tracks[int(k)].avg_feat(), avg, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["seq_T64.npz", "seq_T200.npz", "seq_T70_overlap.npz"])
+def test_sequence_ids_and_boxes_exact_per_stage_cascade(name, monkeypatch):
+    """Same check with the fused cascade kernel off (one cost + assignment launch and one D2H per stage: the path
+    frames with more than 256 detections take)."""
+    monkeypatch.setenv("FM_FUSE_CASCADE", "0")
+    test_sequence_ids_and_boxes_exact(name)
+
+
+@pytest.mark.parametrize("name", ["seq_T64.npz", "seq_T200.npz", "seq_T70_overlap.npz"])
+def test_sequence_ids_and_boxes_exact_always_fused_cascade(name, monkeypatch):
+    """... and with fm_assoc_cascade forced for every update (by default single-stage frames keep the per-stage path)."""
+    monkeypatch.setenv("FM_FUSE_CASCADE", "2")
+    test_sequence_ids_and_boxes_exact(name)
