@@ -126,6 +126,7 @@ __device__ void lsa_warp_solve(const double* __restrict__ cost, int nr0, int nc0
                 if (pos[k] >= 0) c_i[k] = cost[sj[k] + (size_t)i * si];
         }
         if (infeasible) break;
+        __syncwarp();        // lane 0's visit records (s_vrow / s_vmv) -> the lanes that apply them (racecheck, r02)
         // dual updates
         if (lane == 0) s_u[cur] = __dadd_rn(s_u[cur], minVal);
         for (int t = 1 + lane; t < nvis; t += 32) {
