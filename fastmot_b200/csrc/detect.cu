@@ -11,7 +11,8 @@
 
 int fm_launch_nms_scan(const unsigned long long* keys, const float* dense, const int* counter, int key_cap,
                        const unsigned long long* mask, int words, double max_area, double min_ar, int max_out,
-                       double* out_tlbr, long long* out_label, double* out_conf, int* out_count, cudaStream_t s);
+                       double* out_tlbr, long long* out_label, double* out_conf, int* out_count, int* status,
+                       cudaStream_t s);
 
 namespace {
 
@@ -272,7 +273,7 @@ extern "C" int fm_diou_nms_filter(unsigned long long* keys, const float* dense, 
     nms_mask_kernel<<<FM_NUM_SMS * 8, 64, 0, s>>>(keys, dense, counter, key_cap, nms_thresh, mask, words);
     FM_CHECK_LAUNCH("nms_mask_kernel");
     fm_launch_nms_scan(keys, dense, counter, key_cap, mask, words, max_area, min_aspect_ratio, max_out, out_tlbr,
-                       out_label, out_conf, out_count, s);   // blocked scan, detect_nms.cu
+                       out_label, out_conf, out_count, status, s);   // blocked scan, detect_nms.cu
     FM_CHECK_LAUNCH("nms_scan_kernel");
     return FM_OK;
 }

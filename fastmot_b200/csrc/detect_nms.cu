@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_scan_blocked_kernel(const uns
                                                                         int max_out, double* __restrict__ out_tlbr,
                                                                         long long* __restrict__ out_label,
                                                                         double* __restrict__ out_conf,
-                                                                        int* __restrict__ out_count) {
+                                                                        int* __restrict__ out_count, int* __restrict__ status) {
     extern __shared__ unsigned long long sm[];   // removed[nw] | keep[nw] | okbits (u32 x 2nw) | prefix (i32 x 2nw)
     __shared__ unsigned long long s_kept;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -113,7 +113,10 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_scan_blocked_kernel(const uns
             if (w < nw32) prefix[w] = run + inc - cnt;
             run += __shfl_sync(0xffffffffu, inc, 31);
         }
-        if (lane == 0) *out_count = min(run, max_out);
+        if (lane == 0) {
+            *out_count = min(run, max_out);
+            if (run > max_out && status[0] == 0) status[0] = 2;   // more survivors than max_out rows: host raises (no silent drop)
+        }
     }
     __syncthreads();
     for (int i0 = warp << 5; i0 < n; i0 += NMS_THREADS) {
@@ -136,9 +139,10 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_scan_blocked_kernel(const uns
 
 int fm_launch_nms_scan(const unsigned long long* keys, const float* dense, const int* counter, int key_cap,
                        const unsigned long long* mask, int words, double max_area, double min_ar, int max_out,
-                       double* out_tlbr, long long* out_label, double* out_conf, int* out_count, cudaStream_t s) {
+                       double* out_tlbr, long long* out_label, double* out_conf, int* out_count, int* status,
+                       cudaStream_t s) {
     nms_scan_blocked_kernel<<<1, NMS_THREADS, (size_t)(4 * words + 4) * 8, s>>>(keys, dense, counter, key_cap, mask, words,
                                                                      max_area, min_ar, max_out, out_tlbr, out_label,
-                                                                     out_conf, out_count);
+                                                                     out_conf, out_count, status);
     return 0;
 }

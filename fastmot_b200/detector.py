@@ -180,6 +180,9 @@ class YOLODetector(Detector):
         """Waits for the async pipeline and returns np.recarray[DET_DTYPE] (class asc, objectness desc)."""
         self._done.synchronize()
         n, status, n_cand = (int(v) for v in self._h_meta[:3])
+        if status == 2:
+            raise RuntimeError(f"more than max_dets = {self.max_dets} boxes survived NMS and the area / aspect "
+                               "filters; raise max_dets (no silent truncation)")
         if status != 0:
             raise RuntimeError(f"{n_cand} candidates passed conf_thresh but key_cap is {self.key_cap}; "
                                "raise key_cap (no silent truncation)")

@@ -49,6 +49,11 @@ class MOT:
         self.detector_frame_skip = detector_frame_skip
         self.class_ids = tuple(np.unique(class_ids))
         self.draw = draw
+        if draw:
+            # mot.py:166-167,191-196 draw on the host frame with OpenCV; visualisation is outside the GPU hot path
+            # (SURVEY.md §2.1 row 12).  Say so instead of silently ignoring the flag.
+            LOGGER.warning("draw=True: fastmot_b200 has no visualizer (out of scope); frames are left untouched. "
+                           "Use visible_tracks() to draw with your own code.")
         if self.detector_type == DetectorType.SSD:
             raise NotImplementedError("the SSD detector is not on the B200 hot path (SURVEY.md §2.1 row 2)")
         if yolo_detector_cfg is None:

@@ -191,7 +191,8 @@ int fm_yolo_decode_filter(const void* head_out, int is_fp16, int nhwc, int yolo_
 /* Rest of _filter_dets (detector.py:343-365) + diou_nms (rect.py:198-244): sort by (class, objectness desc),
  * per-class DIoU-NMS, to_tlbr rounding, area / aspect-ratio filters.  mask: >= fm_nms_mask_bytes(key_cap) bytes.
  * Outputs (device): out_tlbr[max_out][4] f64, out_label[max_out] i64, out_conf[max_out] f64, out_count[1];
- * status[0] = 1 if more than key_cap candidates passed the threshold (caller must raise). */
+ * status[0] = 1 if more than key_cap candidates passed the threshold, 2 if more than max_out boxes survived (only
+ * the first max_out are written); the caller must raise on either.  key_cap <= 16384 (shared-memory sort). */
 long long fm_nms_mask_bytes(int key_cap);
 int fm_diou_nms_filter(unsigned long long* keys, const float* dense, const int* counter, int key_cap,
                        double nms_thresh, double max_area, double min_aspect_ratio, unsigned long long* mask,
