@@ -272,13 +272,17 @@ class OSNetEngine(_Net):
     L2-normalised embeddings (feature_extractor.py:62-74)."""
 
     def __init__(self, width, weights=None, input_hw=(256, 128), feature_dim=512, max_batch=256, use_tc=True,
-                 use_graph=False):
+                 use_graph=False, ops=None):
+        """`ops` (+ `weights`): an op list in the vocabulary of models/osnet.py, e.g. from
+        models.onnx_import.import_reid_onnx; default: the published OSNet of the given width."""
         super().__init__(use_tc, use_graph)
         # The ReID stack's stand-alone convs are thousands of tiles with 1-8 K slices each: the one-tile-per-CTA TMA
         # kernel pays its per-CTA set-up 20 times per SM there (OSNet x1.0 @200 crops: 2.89 ms with it, 2.66 ms with
         # the cp.async kernel, profiles/r02_summary.md); it is the batch-1 detector layers it was written for.
         self.use_tma = os.environ.get("FM_OSNET_TMA", "0") == "1"
-        self.ops = osnet.build_osnet(width, feature_dim)
+        if ops is not None and weights is None:
+            raise ValueError("a custom op list needs its weights")
+        self.ops = list(ops) if ops is not None else osnet.build_osnet(width, feature_dim)
         self.weights = weights if weights is not None else osnet.synthetic_weights(self.ops)
         self.max_batch = max_batch
         self.feature_dim = feature_dim
@@ -361,7 +365,7 @@ class OSNetEngine(_Net):
                 live[self.ops[1][2]] = (y, 64, 64, 32)
                 skip_until = 1
                 continue
-            if kind == 'conv' and self.fuse_osb and op[1].endswith('.conv1'):
+            if kind == 'conv' and self.fuse_osb and op[4] == 1 and op[7] == 'relu':     # OSBlock candidate (structural)
                 blk = self._match_osblock(k)
                 x, xc, h, w = live[op[8]]
                 if blk is not None and xc == op[2] and xc % 64 == 0 and \
@@ -591,7 +595,7 @@ class OSNetEngine(_Net):
         acc = ops[k][4]
         i = k + 1
         ds = None
-        if i < len(ops) and ops[i][0] == 'conv' and ops[i][1].endswith('.downsample'):
+        if i < len(ops) and ops[i][0] == 'conv' and ops[i][8] != acc:      # a conv beside conv3: the downsample branch
             ds = ops[i]
             i += 1
         if i + 1 >= len(ops):
@@ -641,6 +645,17 @@ class OSNetEngine(_Net):
 
 
 def build_reid_engine(model, max_batch=256, use_tc=True, use_graph=True):
+    """Engine for a `models.ReID` descriptor.  `MODEL_PATH` (an ONNX file, the reference's reid.py:20-23) is lowered
+    by models.onnx_import; without it the descriptor's `ARCH` selects the built-in OSNet with synthetic weights."""
+    if getattr(model, 'MODEL_PATH', None) is not None:
+        from .models.onnx_import import import_reid_onnx
+        ops, weights, in_shape, dim = import_reid_onnx(str(model.MODEL_PATH))
+        if tuple(in_shape) != tuple(model.INPUT_SHAPE):
+            raise ValueError(f"{model.__name__}: ONNX input {in_shape} != INPUT_SHAPE {model.INPUT_SHAPE}")   # reid.py:66
+        if dim != model.OUTPUT_LAYOUT:
+            raise ValueError(f"{model.__name__}: ONNX feature dim {dim} != OUTPUT_LAYOUT {model.OUTPUT_LAYOUT}")
+        return OSNetEngine(None, weights=weights, input_hw=in_shape[1:], feature_dim=dim, max_batch=max_batch,
+                           use_tc=use_tc, use_graph=use_graph, ops=ops)
     arch, width = model.ARCH
     assert arch == 'osnet'
     return OSNetEngine(width, input_hw=model.INPUT_SHAPE[1:], feature_dim=model.OUTPUT_LAYOUT, max_batch=max_batch,

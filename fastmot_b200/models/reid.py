@@ -4,7 +4,8 @@
 class ReID:
     __registry = {}
 
-    ARCH = None          # ('osnet', width multiplier)
+    ARCH = None          # ('osnet', width multiplier): built-in architecture, synthetic weights
+    MODEL_PATH = None    # path to an ONNX file (reid.py:20-23); imported by models/onnx_import.py when set
     WEIGHTS_PATH = None
     INPUT_SHAPE = None
     OUTPUT_LAYOUT = None

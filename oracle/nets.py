@@ -116,7 +116,7 @@ def run_osnet(ops, weights, x, quantize=None):
             w, b = (torch.as_tensor(a) for a in weights[name])
             v = F.relu(bufs[src] @ w.T + b)
             bufs[dst] = v / v.norm(dim=1, keepdim=True)
-    return bufs['feat']
+    return bufs[ops[-1][5]]     # the 'fc' op's destination ('feat' for build_osnet; any name for imported graphs)
 
 
 def fp16_roundtrip(t):

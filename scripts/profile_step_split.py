@@ -6,11 +6,14 @@ import torch
 import bench
 from fastmot_b200 import MOT
 
+from types import SimpleNamespace
 N = 111
-scene, frames = bench.make_frames(0, N)
-mot = MOT(scene.size, detections_override=bench.det_override(scene), **bench._cfg())
+c = bench.CONFIGS[int(os.environ.get("FM_CONFIG", 3))]
+scene = bench.make_scene(c, 0)
+frames = [scene.frame(t) for t in range(N)]
+mot = MOT(scene.size, detections_override=bench.det_override(scene), **bench._cfg(c, SimpleNamespace(p5_input=896)))
 mot.reset(1 / 30.)
-mot.extractors[0]._engine(bench.N_OBJECTS)
+mot.extractors[0]._engine(c["n"])
 dev_frames = [torch.as_tensor(f).cuda() for f in frames]
 for f in dev_frames[:11]:
     mot.step(f)
