@@ -33,6 +33,24 @@ class FmTrackJob(C.Structure):
                 ("redetect", c_i), ("min_dist", c_i), ("scratch_off", c_i), ("eig_max", c_f), ("pad", c_i)]
 
 
+class FmFlowPlan(C.Structure):
+    """include/fastmot_b200.h: FmFlowPlan (field order and types must match)."""
+    _fields_ = [("frame_w", c_i), ("frame_h", c_i), ("gray", c_p * 2), ("pyr", FmPyramid * 2),
+                ("tlbr_pool", c_p), ("slots", c_p), ("owner", c_p), ("kp_pool", c_p), ("kp_prev_pool", c_p),
+                ("kp_count", c_p), ("max_kp", c_i),
+                ("feat_density", c_d), ("feat_dist_factor", c_d), ("quality", c_d), ("max_corners", c_i),
+                ("jobs", c_p), ("scratch", c_p), ("scratch_cap", c_i), ("flags", c_p),
+                ("bg", c_p), ("bg_mask", c_p), ("bg_score", c_p), ("bg_w", c_i), ("bg_h", c_i), ("bg_thresh", c_i),
+                ("unscale_x", c_f), ("unscale_y", c_f), ("bg_pts", c_p), ("bg_count", c_p), ("max_bg", c_i),
+                ("all_prev", c_p), ("all_cur", c_p), ("status", c_p), ("err", c_p), ("trk_begin", c_p), ("meta", c_p),
+                ("max_points", c_i), ("pt_scale_x", c_f), ("pt_scale_y", c_f), ("win_w", c_i), ("win_h", c_i),
+                ("lk_max_count", c_i), ("lk_epsilon", c_f), ("lk_min_eig", c_f), ("max_error", c_f),
+                ("ransac_max_iter", c_i), ("ransac_conf", c_d), ("ransac_thresh", c_d), ("inlier_thresh", c_i),
+                ("refine_iters", c_i), ("good_idx", c_p), ("inl_idx", c_p), ("bg_kp", c_p), ("bg_kp_prev", c_p),
+                ("bg_kp_count", c_p), ("est_boxes", c_p), ("sig", c_p), ("klt_tlbr", c_p), ("klt_ok", c_p),
+                ("klt_ok_bytes", c_ll), ("inlier_ratio", c_p), ("rounds_ahead", c_i)]
+
+
 class FmConvDesc(C.Structure):
     _fields_ = [(k, c_i) for k in ("n", "hi", "wi", "cin", "cin_stride", "cin_offset", "ho", "wo", "cout",
                                    "cout_stride", "cout_offset", "kh", "kw", "stride", "pad", "act", "res_stride",
@@ -99,6 +117,10 @@ SIGNATURES = {
                                     c_p]),
     "fm_ransac_affine_partial_batch": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
                                               c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_d, c_d, c_i, c_i, c_i, c_p]),
+    "fm_flow_plan_create": (c_p, [C.POINTER(FmFlowPlan)]),
+    "fm_flow_plan_destroy": (None, [c_p]),
+    "fm_flow_preprocess": (c_i, [c_p, c_p, c_i, c_p]),
+    "fm_flow_predict": (c_i, [c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p]),
     "fm_conv2d_simt": (c_i, [C.POINTER(FmConvDesc), c_p, c_p, c_p, c_p, c_p, c_p]),
     "fm_maxpool": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p]),
     "fm_maxpool_pad": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p]),

@@ -9,6 +9,7 @@ Kalman kernel reads directly.
 """
 import ctypes as C
 import logging
+import os
 
 import numpy as np
 import torch
@@ -138,12 +139,84 @@ class Flow:
         self._ev_lk = torch.cuda.Event()
         self._ev_h = torch.cuda.Event()
         self.pool = None
+        self._runner = None
         self._order = []
         self._bg_cache = None
         self.rounds_last = 0
 
     def bind_pool(self, pool):
+        if getattr(self, "_runner", None) is not None:
+            self._lib.fm_flow_plan_destroy(self._runner)
         self.pool = pool
+        self._runner = None
+
+    # ------------------------------------------------------------------ one-call runner (csrc/flow_runner.cu)
+    def _plan(self):
+        """Freezes every fixed buffer address and parameter of predict_device into an FmFlowPlan; the per-frame
+        enqueue is then a single C-ABI call (fm_flow_predict).  FM_FLOW_RUNNER=0, or an active stagetime pass (which
+        times the individual entry points), keeps the call-by-call sequence below."""
+        pool = self.pool
+        P = _lib.FmFlowPlan()
+        W, H = self.size
+        P.frame_w, P.frame_h = W, H
+        for k in range(2):
+            P.gray[k] = self.gray[k].data_ptr()
+            C.memmove(C.byref(P.pyr[k]), C.byref(self.pyr_desc[k]), C.sizeof(_lib.FmPyramid))
+        P.tlbr_pool, P.slots, P.owner = pool.tlbr.data_ptr(), self.slots_dev.data_ptr(), self.owner.data_ptr()
+        P.kp_pool, P.kp_prev_pool, P.kp_count, P.max_kp = (pool.kp.data_ptr(), pool.kp_prev.data_ptr(),
+                                                          pool.kp_count.data_ptr(), pool.max_kp)
+        mk = self.obj_feat_params
+        P.feat_density, P.feat_dist_factor = float(self.feat_density), float(self.feat_dist_factor)
+        P.quality, P.max_corners = float(mk["qualityLevel"]), int(mk["maxCorners"])
+        P.jobs, P.scratch, P.scratch_cap, P.flags = (self.jobs.data_ptr(), self.scratch.data_ptr(), self.scratch_cap,
+                                                     self.flags.data_ptr())
+        bw, bh = self.bg_feat_sz
+        P.bg, P.bg_mask, P.bg_score = self.bg.data_ptr(), self.bg_mask.data_ptr(), self.bg_score.data_ptr()
+        P.bg_w, P.bg_h, P.bg_thresh = bw, bh, int(self.bg_feat_thresh)
+        P.unscale_x = float(np.float32(1) / np.float32(self.bg_feat_scale_factor[0]))
+        P.unscale_y = float(np.float32(1) / np.float32(self.bg_feat_scale_factor[1]))
+        P.bg_pts, P.bg_count, P.max_bg = self.bg_pts.data_ptr(), self.bg_count.data_ptr(), self.max_bg
+        P.all_prev, P.all_cur, P.status, P.err = (self.all_prev.data_ptr(), self.all_cur.data_ptr(),
+                                                  self.status.data_ptr(), self.err.data_ptr())
+        P.trk_begin, P.meta, P.max_points = self.trk_begin.data_ptr(), self.meta.data_ptr(), self.max_points
+        win, crit = self.opt_flow_params["winSize"], self.opt_flow_params["criteria"]
+        P.pt_scale_x, P.pt_scale_y = float(self.opt_flow_scale_factor[0]), float(self.opt_flow_scale_factor[1])
+        P.win_w, P.win_h, P.lk_max_count = int(win[0]), int(win[1]), int(crit[1])
+        P.lk_epsilon, P.lk_min_eig, P.max_error = float(crit[2]), 1e-4, float(self.max_error)
+        P.ransac_max_iter, P.ransac_conf, P.ransac_thresh = int(self.ransac_max_iter), float(self.ransac_conf), 3.0
+        P.inlier_thresh, P.refine_iters = int(self.inlier_thresh), 10
+        P.good_idx, P.inl_idx = self.good_idx.data_ptr(), self.inl_idx.data_ptr()
+        P.bg_kp, P.bg_kp_prev, P.bg_kp_count = (self.bg_kp.data_ptr(), self.bg_kp_prev.data_ptr(),
+                                                self.bg_kp_count.data_ptr())
+        P.est_boxes, P.sig = self.est_boxes.data_ptr(), self.sig.data_ptr()
+        P.klt_tlbr, P.klt_ok = pool.klt_tlbr.data_ptr(), pool.klt_ok.data_ptr()
+        P.klt_ok_bytes = pool.klt_ok.numel() * pool.klt_ok.element_size()
+        P.inlier_ratio = pool.inlier_ratio.data_ptr()
+        P.rounds_ahead = self.ROUNDS_AHEAD
+        return P
+
+    def _get_runner(self):
+        if not self.USE_RUNNER or self.pool is None:
+            return None
+        from . import stagetime
+        if stagetime.active():
+            return None
+        if self._runner is None:
+            h = self._lib.fm_flow_plan_create(C.byref(self._plan()))
+            if not h:
+                raise _lib.FastMOTLibError("fm_flow_plan_create: " + self._lib.fm_last_error().decode(errors="replace"))
+            self._runner = C.c_void_p(h)
+        return self._runner
+
+    def __del__(self):
+        h = getattr(self, "_runner", None)
+        if h is not None:
+            try:
+                self._lib.fm_flow_plan_destroy(h)
+            except Exception:
+                pass
+
+    USE_RUNNER = os.environ.get("FM_FLOW_RUNNER", "1") != "0"
 
     # ------------------------------------------------------------------ lazily fetched attributes
     def _fetch_bg(self):
@@ -191,7 +264,6 @@ class Flow:
         s = stream_ptr()
         cur = 1 - self.prev
         frame_dev = self._to_device(frame)
-        self._preprocess(frame_dev, cur)
         # order tracks from closest to farthest (flow.py:157; Python's stable sort on Track.__lt__)
         # Track.__lt__ compares (tlbr[-1], -age); sorting on that key gives the identical (stable) order without a
         # Python-level __lt__ call per comparison (0.45 ms per frame at 200 tracks)
@@ -203,6 +275,20 @@ class Flow:
         if n:
             self._h_slots[:n] = torch.as_tensor(np.fromiter((t.slot for t in tracks), np.int32, n))
             self.slots_dev[:n].copy_(self._h_slots[:n], non_blocking=True)
+        runner = self._get_runner()
+        if runner is not None:
+            main = torch.cuda.current_stream()
+            _lib.check(lib.fm_flow_predict(runner, ptr(frame_dev), self.prev, n, ptr(h_dev), ptr(h_ok_dev),
+                                           C.c_void_p(main.cuda_stream), C.c_void_p(self._side.cuda_stream)),
+                       "fm_flow_predict")
+            self.prev = cur                      # flow.py:212-213
+            self._bg_cache = None
+            self._affine_args = (n, W, H)
+            self.rounds_last = self.ROUNDS_AHEAD
+            if not self.defer_sync:
+                self.finish_rounds(self.ROUNDS_AHEAD)
+            return self._order
+        self._preprocess(frame_dev, cur)
         pool.klt_ok.zero_()
         fl = self.flags.data_ptr()
         mk = self.obj_feat_params

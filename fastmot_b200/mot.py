@@ -82,6 +82,11 @@ class MOT:
         self._uploader = FrameUploader(size, depth=3)
         self._det_stream = torch.cuda.Stream()
         self._main_ready = torch.cuda.Event()
+        # ReID crops + OSNet run on their own stream so that the batched Kalman step, its read-back and the host side
+        # of the association set-up proceed under the OSNet forward (mot.py:147-156: the reference overlaps the
+        # extractor's GPU work with apply_kalman on the CPU the same way)
+        self._reid_stream = torch.cuda.Stream()
+        self._reid_done = torch.cuda.Event()
         # Optional callable frame_id -> recarray[DET_DTYPE]: replaces the detector's OUTPUT after the full
         # detector pipeline has run (synthetic-weight benchmarking: random weights cannot detect).
         self.detections_override = detections_override
@@ -136,10 +141,17 @@ class MOT:
                 detections = self._detections()
             with Profiler('extract'):
                 cls_bboxes = self._split_bboxes_by_cls(detections.tlbr, detections.label, self.class_ids)
-                for extractor, bboxes in zip(self.extractors, cls_bboxes):
-                    extractor.extract_async(frame_dev, bboxes)
+                main = torch.cuda.current_stream()
+                with torch.cuda.stream(self._reid_stream):
+                    # _main_ready (recorded by _detect_async on the main stream at the top of this step) orders the
+                    # crops after the frame upload and after everything the previous update read from the engines
+                    self._reid_stream.wait_event(self._main_ready)
+                    for extractor, bboxes in zip(self.extractors, cls_bboxes):
+                        extractor.extract_async(frame_dev, bboxes)
+                    self._reid_done.record(self._reid_stream)
                 with Profiler('track', aggregate=True):
                     self.tracker.apply_kalman()
+                main.wait_event(self._reid_done)         # embeddings feed the association kernels on the main stream
                 embeddings = [extractor.postprocess() for extractor in self.extractors]
                 if len(embeddings) > 1:
                     embeddings = np.concatenate([np.asarray(e) for e in embeddings])

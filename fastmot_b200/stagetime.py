@@ -49,6 +49,11 @@ def enable():
         setattr(lib, name, wrapper)
 
 
+def active():
+    """True while the per-entry-point wrappers are installed (Flow then keeps its call-by-call sequence)."""
+    return bool(_saved)
+
+
 def disable():
     lib = _lib.load()
     for name, fn in _saved.items():

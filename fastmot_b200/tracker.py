@@ -276,13 +276,13 @@ class MultiTracker:
         if not n:
             return
         tlbrs = res[2].copy()
-        lost = res[3]
-        for k, (trk_id, track) in enumerate(items):
-            track.update(tlbrs[k])
-            if lost[k]:
-                if track.confirmed:
-                    LOGGER.info(f"{'Out:':<14}{track}")
-                self._mark_lost(trk_id)
+        for (_, track), tlbr in zip(items, tlbrs):      # Track.update (track.py:108): the predicted box joins the history
+            track.bboxes.append(tlbr)
+        for k in np.nonzero(res[3])[0].tolist():        # tracks that left the frame (tracker.py:176-181), in dict order
+            trk_id, track = items[k]
+            if track.confirmed:
+                LOGGER.info(f"{'Out:':<14}{track}")
+            self._mark_lost(trk_id)
 
     def _copy_status(self, p_hok, p_H):
         s = stream_ptr()

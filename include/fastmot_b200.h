@@ -345,6 +345,72 @@ int fm_ransac_affine_partial_batch(const float* all_prev, const float* all_cur, 
                                    int max_iters, double confidence, double thresh, int inlier_thresh,
                                    int refine_iters, int first_round, void* stream);
 
+/* ---- KLT stage runner: Flow.predict (flow.py:135-264) as ONE call -------------------------------------------
+ * fm_flow_plan_create copies the plan (all pointers are caller-owned device buffers that stay fixed between frames;
+ * the fields are the arguments of the per-call functions above, named alike) and creates two private events;
+ * fm_flow_predict enqueues, on s_main: gray + 0.5x + pyramid + Scharr of `frame` into buffer 1 - prev, klt_ok clear,
+ * fm_flow_keypoints / fm_bg_small / fm_fast_detect / fm_gather_points on buffer prev, fm_lk_track prev -> cur, then
+ * fm_ransac_homography on s_side (forked / joined with the private events) next to rounds_ahead (a multiple of 4)
+ * rounds of fm_ransac_affine_partial_batch on s_main.  Identical launches to the per-call sequence; no allocation,
+ * no synchronisation.  flags: int[32] = {scratch counter, keypoint status, -, .., [8..23] round flags}. */
+typedef struct FmFlowPlan {
+    int frame_w, frame_h;
+    unsigned char* gray[2];
+    FmPyramid pyr[2];
+    const double* tlbr_pool;
+    const int* slots;
+    int* owner;
+    float* kp_pool;
+    float* kp_prev_pool;
+    int* kp_count;
+    int max_kp;
+    double feat_density, feat_dist_factor, quality;
+    int max_corners;
+    FmTrackJob* jobs;
+    float* scratch;
+    int scratch_cap;
+    int* flags;
+    unsigned char* bg;
+    unsigned char* bg_mask;
+    unsigned char* bg_score;
+    int bg_w, bg_h, bg_thresh;
+    float unscale_x, unscale_y;
+    float* bg_pts;
+    int* bg_count;
+    int max_bg;
+    float* all_prev;
+    float* all_cur;
+    unsigned char* status;
+    float* err;
+    int* trk_begin;
+    int* meta;
+    int max_points;
+    float pt_scale_x, pt_scale_y;
+    int win_w, win_h, lk_max_count;
+    float lk_epsilon, lk_min_eig, max_error;
+    int ransac_max_iter;
+    double ransac_conf, ransac_thresh;
+    int inlier_thresh, refine_iters;
+    int* good_idx;
+    int* inl_idx;
+    float* bg_kp;
+    float* bg_kp_prev;
+    int* bg_kp_count;
+    int* est_boxes;
+    unsigned long long* sig;
+    double* klt_tlbr;
+    unsigned char* klt_ok;
+    long long klt_ok_bytes;
+    double* inlier_ratio;
+    int rounds_ahead;
+} FmFlowPlan;
+void* fm_flow_plan_create(const FmFlowPlan* plan);      /* NULL on error (fm_last_error) */
+void fm_flow_plan_destroy(void* handle);
+/* flow.py:121-133 / :153-154 for buffer k (0 / 1) */
+int fm_flow_preprocess(void* handle, const unsigned char* frame, int k, void* stream);
+int fm_flow_predict(void* handle, const unsigned char* frame, int prev, int n_trk, double* H_out, int* h_ok,
+                    void* s_main, void* s_side);
+
 /* ---------------------------------------------------------------- tensor-core primitive self-test ----------- */
 /* One CTA exercises the building blocks of the fused kernels (csrc/tc_common.cuh): TMA tensor-map load of a
  * [128 x 64] fp16 tile (rows row0.. of a [rows][64] matrix; rows past the end read as zero) into 128-byte-swizzled

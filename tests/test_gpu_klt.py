@@ -284,3 +284,52 @@ def test_keypoint_maintenance_vs_goodFeaturesToTrack(overlap, n_obj):
     # background FAST points follow the per-track blocks
     bg_got = pts[begins[len(order)]:begins[len(order)] + (len(dbg['all_prev']) - dbg['bg_begin'])]
     assert np.array_equal(bg_got, dbg['all_prev'][dbg['bg_begin']:])
+
+
+def test_flow_runner_equals_call_by_call_sequence(monkeypatch):
+    """fm_flow_predict (one C-ABI call per frame, csrc/flow_runner.cu) must enqueue exactly what the call-by-call
+    sequence of Flow.predict_device enqueues: identical homographies, KLT boxes, keypoints and track boxes, bit for bit,
+    over a sequence with detector updates."""
+    from fastmot_b200 import MultiTracker
+    from fastmot_b200.flow import Flow
+    from fastmot_b200.synth import SyntheticScene
+    from oracle.run import default_tracker_cfg
+    scene = SyntheticScene(80, seed=21, label=0, overlap=True, dropout_frames=(10,))
+    frames = [scene.frame(t) for t in range(14)]
+
+    def run(use_runner):
+        monkeypatch.setattr(Flow, "USE_RUNNER", use_runner)
+        trk = MultiTracker(scene.size, 'cosine', **default_tracker_cfg())
+        trk.reset(1 / 30)
+        out = []
+        for t, frame in enumerate(frames):
+            if t == 0:
+                tl, lb, cf, _ = scene.detections(0)
+                trk.init(frame, _dets(tl, lb, cf))
+                continue
+            trk.compute_flow(frame)
+            assert (trk.flow._runner is not None) == use_runner
+            trk.apply_kalman()
+            klt = trk.klt_bboxes
+            kps = {k: v.keypoints.copy() for k, v in list(trk.tracks.items())[:10]}
+            if t % 5 == 0:
+                tl, lb, cf, ids = scene.detections(t)
+                trk.update(t, _dets(tl, lb, cf), scene.embeddings(ids, t))
+            out.append((trk.homography.copy(), {k: v.copy() for k, v in klt.items()}, kps,
+                        {k: v.tlbr.copy() for k, v in trk.tracks.items()}, trk.flow.bg_keypoints.copy()))
+        return out
+
+    a, b = run(True), run(False)
+    assert len(a) == len(b) == 13
+    for (ha, ka, pa, ta, ba), (hb, kb, pb, tb, bb) in zip(a, b):
+        np.testing.assert_array_equal(ha, hb)
+        assert set(ka) == set(kb) and len(ka) > 40
+        for k in ka:
+            np.testing.assert_array_equal(ka[k], kb[k])
+        assert set(pa) == set(pb)
+        for k in pa:
+            np.testing.assert_array_equal(pa[k], pb[k])
+        assert set(ta) == set(tb)
+        for k in ta:
+            np.testing.assert_array_equal(ta[k], tb[k])
+        np.testing.assert_array_equal(ba, bb)
