@@ -123,14 +123,24 @@ def make_scene(c, seed):
                           overlap=bool(c.get("overlap")))
 
 
-def det_override(scene):
+def det_override(scene, upto=0):
+    """frame id -> scripted detections.  The rows for frames [0, upto) are generated up front: producing the synthetic
+    ground truth is the harness' job, not part of the measured step."""
     from fastmot_b200.detector import DET_DTYPE
+    cache = {}
 
-    def f(t):
+    def make(t):
         tl, lb, cf, _ = scene.detections(t)
         d = np.zeros(len(tl), DET_DTYPE)
         d['tlbr'], d['label'], d['conf'] = tl, lb, cf
         return d.view(np.recarray)
+
+    for t in range(upto):
+        cache[t] = make(t)
+
+    def f(t):
+        d = cache.get(t)
+        return make(t) if d is None else d.copy()
     return f
 
 
@@ -245,7 +255,7 @@ def run_ours(args):
 
     if c["kind"] == "mot":
         from fastmot_b200 import MOT
-        mot = MOT(scene.size, detections_override=det_override(scene), **_cfg(c, args))
+        mot = MOT(scene.size, detections_override=det_override(scene, total), **_cfg(c, args))
         mot.extractors[0]._engine(c["n"])      # build + warm the ReID engine outside the timed region
         for e in [mot.detector.backend] + list(mot.extractors[0]._engines.values()):
             e.warm(3)
@@ -262,7 +272,7 @@ def run_ours(args):
     else:
         from fastmot_b200 import MultiTracker
         from fastmot_b200.config import default_tracker_cfg
-        dets = det_override(scene)
+        dets = det_override(scene, total)
         trk = MultiTracker(scene.size, 'cosine', **{k: v for k, v in default_tracker_cfg().items() if k != 'flow_cfg'})
         state = {"t": 0}
 

@@ -7,11 +7,67 @@
 #include "../../include/fastmot_b200.h"
 #include <new>
 
+#include <stdlib.h>
+
 namespace {
 struct FlowRunner {
     FmFlowPlan p;
     cudaEvent_t ev_lk = nullptr, ev_h = nullptr;
+    // pyramid + Scharr chain of buffer k as a CUDA graph: pyrDown levels on one branch, the Scharr images on a second
+    // (each needs only its own level), one launch instead of 2 * levels - 1.  0 = not built, 1 = ready, -1 = unavailable
+    cudaGraphExec_t pyr_graph[2] = {nullptr, nullptr};
+    int pyr_state[2] = {0, 0};
+    int pyr_nodes = 0;
 };
+
+bool pyr_graph_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("FM_PYR_GRAPH");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on != 0;
+}
+
+// Records pyr_level / scharr of buffer k into a graph by stream capture on two private streams.  Any failure leaves
+// the runner on plain launches (state -1); nothing here touches the caller's streams.
+void build_pyr_graph(FlowRunner* r, int k) {
+    const FmPyramid& py = r->p.pyr[k];
+    r->pyr_state[k] = -1;
+    cudaStream_t s1 = nullptr, s2 = nullptr;
+    cudaEvent_t ev[FM_MAX_PYR_LEVELS + 1] = {};
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i <= py.n_levels; ++i) ok = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) == cudaSuccess;
+    if (ok && cudaStreamBeginCapture(s1, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        int nodes = 0;
+        for (int i = 0; ok && i < py.n_levels; ++i) {
+            ok = cudaEventRecord(ev[i], s1) == cudaSuccess && cudaStreamWaitEvent(s2, ev[i], 0) == cudaSuccess &&
+                 fm_scharr(py.img[i], py.w[i], py.h[i], (short*)py.deriv[i], s2) == FM_OK;
+            ++nodes;
+            if (ok && i + 1 < py.n_levels) {
+                ok = fm_pyr_level(py.img[i], py.w[i], py.h[i], (unsigned char*)py.img[i + 1], s1) == FM_OK;
+                ++nodes;
+            }
+        }
+        ok = ok && cudaEventRecord(ev[py.n_levels], s2) == cudaSuccess &&
+             cudaStreamWaitEvent(s1, ev[py.n_levels], 0) == cudaSuccess;
+        const cudaError_t e = cudaStreamEndCapture(s1, &graph);       // always end the capture, even after a failure
+        ok = ok && e == cudaSuccess && graph != nullptr;
+        if (ok && cudaGraphInstantiate(&r->pyr_graph[k], graph, 0) == cudaSuccess) {
+            r->pyr_state[k] = 1;
+            r->pyr_nodes = nodes;
+        }
+        fm_count_launches(-nodes);                                    // recording is not launching
+    }
+    if (graph) cudaGraphDestroy(graph);
+    for (int i = 0; i <= FM_MAX_PYR_LEVELS; ++i)
+        if (ev[i]) cudaEventDestroy(ev[i]);
+    if (s1) cudaStreamDestroy(s1);
+    if (s2) cudaStreamDestroy(s2);
+    cudaGetLastError();
+}
 }  // namespace
 
 extern "C" void* fm_flow_plan_create(const FmFlowPlan* plan) {
@@ -39,6 +95,8 @@ extern "C" void fm_flow_plan_destroy(void* h) {
     if (!r) return;
     cudaEventDestroy(r->ev_lk);
     cudaEventDestroy(r->ev_h);
+    for (int k = 0; k < 2; ++k)
+        if (r->pyr_graph[k]) cudaGraphExecDestroy(r->pyr_graph[k]);
     delete r;
 }
 
@@ -66,6 +124,14 @@ extern "C" int fm_flow_preprocess(void* h, const unsigned char* frame, int k, vo
     const FmFlowPlan& p = r->p;
     const FmPyramid& py = p.pyr[k];
     FM_TRY(fm_gray_half(frame, p.frame_w, p.frame_h, p.gray[k], (unsigned char*)py.img[0], stream));
+    if (pyr_graph_enabled()) {
+        if (r->pyr_state[k] == 0) build_pyr_graph(r, k);
+        if (r->pyr_state[k] == 1) {
+            FM_CUDA_TRY(cudaGraphLaunch(r->pyr_graph[k], (cudaStream_t)stream), "fm_flow_preprocess: pyramid graph");
+            fm_count_launches(r->pyr_nodes);
+            return FM_OK;
+        }
+    }
     for (int i = 0; i < py.n_levels; ++i) {
         if (i + 1 < py.n_levels)
             FM_TRY(fm_pyr_level(py.img[i], py.w[i], py.h[i], (unsigned char*)py.img[i + 1], stream));

@@ -344,59 +344,64 @@ __global__ void fast_score_kernel(const unsigned char* __restrict__ img, int w, 
 }
 
 // NMS (strictly greater than the 8 neighbours), pixel mask, row-major ordered compaction; single CTA.
+// Warp w owns a contiguous run of 32-pixel words; lanes read consecutive pixels (coalesced), the keep decision of
+// every pixel is taken once and kept as one ballot word in shared memory, so the ordered scatter only replays bits.
+#define FAST_NMS_MAX_WORDS 4096      // 131 072 pixels at the background scale (1920x1080 x 0.1^2 = 20 736)
 __global__ void __launch_bounds__(1024) fast_nms_kernel(const unsigned char* __restrict__ score,
                                                          const unsigned char* __restrict__ mask, int w, int h,
                                                          float unscale_x, float unscale_y, float* __restrict__ out_pts,
                                                          int* __restrict__ out_count, int max_pts) {
+    __shared__ unsigned s_bits[FAST_NMS_MAX_WORDS];
     __shared__ int s_warp[32];
-    __shared__ int s_base;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n = w * h;
-    const int chunk = (n + blockDim.x - 1) / blockDim.x;
-    const int beg = tid * chunk, end = min(beg + chunk, n);
-    auto is_kp = [&](int i) {
-        const int y = i / w, x = i - y * w;
-        const int s = score[i];
-        if (s == 0) return false;
-        // neighbours outside [3, w-3) are never corners and have score 0
-        bool ok = s > score[i - 1] && s > score[i + 1] && s > score[i - w - 1] && s > score[i - w] &&
-                  s > score[i - w + 1] && s > score[i + w - 1] && s > score[i + w] && s > score[i + w + 1];
-        return ok && mask[y * w + x] != 0;
-    };
-    int cnt = 0;
-    for (int i = beg; i < end; ++i) cnt += is_kp(i);
-    // block exclusive scan of cnt
-    int v = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += t;
+    const int words = (n + 31) >> 5;
+    const int per_warp = (words + 31) >> 5;               // 32 warps
+    const int w_beg = wid * per_warp, w_end = min(w_beg + per_warp, words);
+    int cnt = 0;                                           // identical in every lane of the warp
+    for (int wd = w_beg; wd < w_end; ++wd) {
+        const int i = (wd << 5) + lane;
+        bool ok = false;
+        if (i < n) {
+            const int sc = score[i];
+            if (sc != 0) {
+                // neighbours outside [3, w-3) x [3, h-3) are never corners and have score 0
+                ok = sc > score[i - 1] && sc > score[i + 1] && sc > score[i - w - 1] && sc > score[i - w] &&
+                     sc > score[i - w + 1] && sc > score[i + w - 1] && sc > score[i + w] && sc > score[i + w + 1] &&
+                     mask[i] != 0;
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) s_bits[wd] = bal;
+        cnt += __popc(bal);
     }
-    if (lane == 31) s_warp[wid] = v;
+    if (lane == 0) s_warp[wid] = cnt;
     __syncthreads();
-    if (wid == 0) {
+    if (wid == 0) {                                        // inclusive scan of the 32 warp totals
         int t = s_warp[lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            int u = __shfl_up_sync(0xffffffffu, t, o);
+            const int u = __shfl_up_sync(0xffffffffu, t, o);
             if (lane >= o) t += u;
         }
         s_warp[lane] = t;
+        if (lane == 31) *out_count = min(t, max_pts);
     }
     __syncthreads();
-    int off = v - cnt + (wid ? s_warp[wid - 1] : 0);
-    if (tid == blockDim.x - 1) *out_count = min(off + cnt, max_pts);
-    for (int i = beg; i < end; ++i) {
-        if (is_kp(i)) {
-            if (off < max_pts) {
+    int off = wid ? s_warp[wid - 1] : 0;
+    for (int wd = w_beg; wd < w_end; ++wd) {
+        const unsigned bal = s_bits[wd];
+        if ((bal >> lane) & 1u) {
+            const int pos = off + __popc(bal & ((1u << lane) - 1u));
+            if (pos < max_pts) {
+                const int i = (wd << 5) + lane;
                 const int y = i / w, x = i - y * w;
-                out_pts[2 * off] = (float)x * unscale_x;      // _unscale_pts (flow.py:335-344)
-                out_pts[2 * off + 1] = (float)y * unscale_y;
+                out_pts[2 * pos] = (float)x * unscale_x;      // _unscale_pts (flow.py:335-344)
+                out_pts[2 * pos + 1] = (float)y * unscale_y;
             }
-            ++off;
         }
+        off += __popc(bal);
     }
-    (void)s_base;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -470,6 +475,7 @@ extern "C" int fm_fast_detect(const unsigned char* img, const unsigned char* mas
                               int max_pts, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid(fm_cdiv(w, 128), h);
+    FM_REQUIRE((long long)w * h <= 32ll * FAST_NMS_MAX_WORDS, "fm_fast_detect: image larger than 131072 pixels");
     fast_score_kernel<<<grid, 128, 0, s>>>(img, w, h, threshold, score);
     fast_nms_kernel<<<1, 1024, 0, s>>>(score, mask, w, h, unscale_x, unscale_y, out_pts, out_count, max_pts);
     FM_CHECK_LAUNCH("fm_fast_detect");
