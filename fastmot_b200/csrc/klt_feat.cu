@@ -344,40 +344,63 @@ __global__ void fast_score_kernel(const unsigned char* __restrict__ img, int w, 
 }
 
 // NMS (strictly greater than the 8 neighbours), pixel mask, row-major ordered compaction; single CTA.
-// Warp w owns a contiguous run of 32-pixel words; lanes read consecutive pixels (coalesced), the keep decision of
-// every pixel is taken once and kept as one ballot word in shared memory, so the ordered scatter only replays bits.
+// Pixels are cut into 32-pixel words; warp w takes words w, w + 32, ... (lanes read consecutive pixels, four words'
+// scores are in flight at once), the keep decision of every pixel is taken once and kept as a ballot word in shared
+// memory; a block scan over the word popcounts gives every word its output offset, the scatter only replays bits.
 #define FAST_NMS_MAX_WORDS 4096      // 131 072 pixels at the background scale (1920x1080 x 0.1^2 = 20 736)
 __global__ void __launch_bounds__(1024) fast_nms_kernel(const unsigned char* __restrict__ score,
                                                          const unsigned char* __restrict__ mask, int w, int h,
                                                          float unscale_x, float unscale_y, float* __restrict__ out_pts,
                                                          int* __restrict__ out_count, int max_pts) {
     __shared__ unsigned s_bits[FAST_NMS_MAX_WORDS];
+    __shared__ int s_pref[FAST_NMS_MAX_WORDS];
     __shared__ int s_warp[32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n = w * h;
     const int words = (n + 31) >> 5;
-    const int per_warp = (words + 31) >> 5;               // 32 warps
-    const int w_beg = wid * per_warp, w_end = min(w_beg + per_warp, words);
-    int cnt = 0;                                           // identical in every lane of the warp
-    for (int wd = w_beg; wd < w_end; ++wd) {
-        const int i = (wd << 5) + lane;
-        bool ok = false;
-        if (i < n) {
-            const int sc = score[i];
-            if (sc != 0) {
-                // neighbours outside [3, w-3) x [3, h-3) are never corners and have score 0
-                ok = sc > score[i - 1] && sc > score[i + 1] && sc > score[i - w - 1] && sc > score[i - w] &&
-                     sc > score[i - w + 1] && sc > score[i + w - 1] && sc > score[i + w] && sc > score[i + w + 1] &&
+    for (int base = wid; base < words; base += 32 * 4) {
+        int sc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int wd = base + 32 * u;
+            const int i = (wd << 5) + lane;
+            sc[u] = (wd < words && i < n) ? (int)score[i] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int wd = base + 32 * u;              // warp-uniform
+            if (wd >= words) break;
+            const int i = (wd << 5) + lane;
+            bool ok = false;
+            if (sc[u] != 0) {
+                // a non-zero score is an interior pixel; neighbours outside [3, w-3) x [3, h-3) have score 0
+                const int v = sc[u];
+                ok = v > score[i - 1] && v > score[i + 1] && v > score[i - w - 1] && v > score[i - w] &&
+                     v > score[i - w + 1] && v > score[i + w - 1] && v > score[i + w] && v > score[i + w + 1] &&
                      mask[i] != 0;
             }
+            const unsigned bal = __ballot_sync(0xffffffffu, ok);
+            if (lane == 0) s_bits[wd] = bal;
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) s_bits[wd] = bal;
-        cnt += __popc(bal);
     }
-    if (lane == 0) s_warp[wid] = cnt;
     __syncthreads();
-    if (wid == 0) {                                        // inclusive scan of the 32 warp totals
+    // exclusive prefix of the word popcounts: thread t owns words 4t .. 4t+3
+    int c[4], tot = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int wd = 4 * tid + u;
+        c[u] = wd < words ? __popc(s_bits[wd]) : 0;
+        tot += c[u];
+    }
+    int v = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    if (lane == 31) s_warp[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
         int t = s_warp[lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -388,11 +411,18 @@ __global__ void __launch_bounds__(1024) fast_nms_kernel(const unsigned char* __r
         if (lane == 31) *out_count = min(t, max_pts);
     }
     __syncthreads();
-    int off = wid ? s_warp[wid - 1] : 0;
-    for (int wd = w_beg; wd < w_end; ++wd) {
+    int run = v - tot + (wid ? s_warp[wid - 1] : 0);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int wd = 4 * tid + u;
+        if (wd < words) s_pref[wd] = run;
+        run += c[u];
+    }
+    __syncthreads();
+    for (int wd = wid; wd < words; wd += 32) {
         const unsigned bal = s_bits[wd];
         if ((bal >> lane) & 1u) {
-            const int pos = off + __popc(bal & ((1u << lane) - 1u));
+            const int pos = s_pref[wd] + __popc(bal & ((1u << lane) - 1u));
             if (pos < max_pts) {
                 const int i = (wd << 5) + lane;
                 const int y = i / w, x = i - y * w;
@@ -400,7 +430,6 @@ __global__ void __launch_bounds__(1024) fast_nms_kernel(const unsigned char* __r
                 out_pts[2 * pos + 1] = (float)y * unscale_y;
             }
         }
-        off += __popc(bal);
     }
 }
 

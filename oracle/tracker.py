@@ -253,7 +253,7 @@ class OracleTracker:
 
     def init(self, frame, tlbr, labels):
         self.tracks.clear()
-        if self.flow is not None:
+        if self.flow is not None and frame is not None:     # frame None: KLT-bypassed association runs (no image)
             self.flow.init(frame)
         for b, l in zip(tlbr, labels):
             self._spawn(0, np.asarray(b, np.float64), int(l))
