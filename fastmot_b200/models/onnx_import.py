@@ -12,7 +12,8 @@ backbones in eval mode):
   GlobalAveragePool -> Conv1x1 -> Relu -> Conv1x1 -> Sigmoid -> Mul(x, .)      -> channel gate; a sum (Add tree) of
       gated tensors lowers to 'gate4' (four streams sharing one gate: the OSBlock) or a chain of 'gate' ops
   Add + Relu                                                                   -> 'add_relu'
-  Flatten / Reshape / Squeeze of the pooled vector, Identity, Dropout         -> aliases
+  Flatten / Reshape / Squeeze of the pooled vector, Identity, Dropout,
+  all-zero Pad (opset-9 AveragePool), Shape / Gather / Unsqueeze / Concat / Constant feeding that Reshape -> aliases / ignored
   Gemm | MatMul + Add  [+ BatchNormalization] + Relu                           -> 'fc' (the engine L2-normalises the
       rows afterwards, feature_extractor.py:62-74 `_normalize`)
 Anything else raises `UnsupportedOnnx` naming the node — never a silent skip.
@@ -279,7 +280,7 @@ class _Lowering:
         self.channels[out] = cout
 
     # -------------------------------------------------------------------------------------------- driver
-    _SHAPE_JUNK = ('Shape', 'Gather', 'Unsqueeze', 'Concat', 'Constant', 'Cast')
+    _SHAPE_JUNK = ('Shape', 'Gather', 'Unsqueeze', 'Concat', 'Cast')
 
     def run(self):
         for n in self.g.nodes:
@@ -297,6 +298,17 @@ class _Lowering:
             elif t in ('Gemm', 'MatMul'):
                 self._fc(n)
             elif t in ('Flatten', 'Reshape', 'Squeeze', 'Identity', 'Dropout'):
+                self.alias[n.outputs[0]] = n.inputs[0]
+            elif t == 'Constant':
+                if isinstance(n.attrs.get('value'), np.ndarray):
+                    self.init[n.outputs[0]] = n.attrs['value']      # e.g. the pads operand of a Pad node
+            elif t == 'Pad':
+                # opset-9 exporters put an explicit all-zero Pad in front of AveragePool: a no-op
+                pads = n.attrs.get('pads')
+                if pads is None and len(n.inputs) > 1 and n.inputs[1] in self.init:
+                    pads = np.asarray(self.init[n.inputs[1]]).reshape(-1).tolist()
+                if pads is None or any(int(p) != 0 for p in pads):
+                    raise UnsupportedOnnx(f"Pad '{n.name}' with pads {pads} (only the all-zero Pad of old exporters)")
                 self.alias[n.outputs[0]] = n.inputs[0]
             elif t in self._SHAPE_JUNK:
                 continue            # shape arithmetic feeding a Reshape of the pooled vector (old exporters)

@@ -218,6 +218,143 @@ def test_plain_residual_backbone_and_gate_chain():
     assert np.abs(got - y).max() < 2e-5, np.abs(got - y).max()
 
 
+# ---- a torchreid-style OSNet written with torch.nn (Zhou et al. ICCV'19 / torchreid osnet.py module structure), used
+# only to obtain a GENUINE torch.onnx.export file: the importer is then checked against the torch forward itself.
+import torch.nn as nn
+
+
+class _ConvLayer(nn.Module):
+    def __init__(self, i, o, k, stride=1, pad=0):
+        super().__init__()
+        self.conv, self.bn = nn.Conv2d(i, o, k, stride, pad, bias=False), nn.BatchNorm2d(o)
+
+    def forward(self, x):
+        return F.relu(self.bn(self.conv(x)))
+
+
+class _Conv1x1Linear(nn.Module):
+    def __init__(self, i, o):
+        super().__init__()
+        self.conv, self.bn = nn.Conv2d(i, o, 1, bias=False), nn.BatchNorm2d(o)
+
+    def forward(self, x):
+        return self.bn(self.conv(x))
+
+
+class _LightConv3x3(nn.Module):
+    def __init__(self, i, o):
+        super().__init__()
+        self.conv1 = nn.Conv2d(i, o, 1, bias=False)
+        self.conv2 = nn.Conv2d(o, o, 3, 1, 1, bias=False, groups=o)
+        self.bn = nn.BatchNorm2d(o)
+
+    def forward(self, x):
+        return F.relu(self.bn(self.conv2(self.conv1(x))))
+
+
+class _ChannelGate(nn.Module):
+    def __init__(self, c, r=16):
+        super().__init__()
+        self.gap, self.fc1, self.fc2 = nn.AdaptiveAvgPool2d(1), nn.Conv2d(c, c // r, 1), nn.Conv2d(c // r, c, 1)
+
+    def forward(self, x):
+        return x * torch.sigmoid(self.fc2(F.relu(self.fc1(self.gap(x)))))
+
+
+class _OSBlock(nn.Module):
+    def __init__(self, i, o):
+        super().__init__()
+        m = o // 4
+        self.conv1 = _ConvLayer(i, m, 1)
+        self.conv2a = _LightConv3x3(m, m)
+        self.conv2b = nn.Sequential(*[_LightConv3x3(m, m) for _ in range(2)])
+        self.conv2c = nn.Sequential(*[_LightConv3x3(m, m) for _ in range(3)])
+        self.conv2d = nn.Sequential(*[_LightConv3x3(m, m) for _ in range(4)])
+        self.gate, self.conv3 = _ChannelGate(m), _Conv1x1Linear(m, o)
+        self.downsample = _Conv1x1Linear(i, o) if i != o else None
+
+    def forward(self, x):
+        identity, x1 = x, self.conv1(x)
+        x2 = self.gate(self.conv2a(x1)) + self.gate(self.conv2b(x1)) + self.gate(self.conv2c(x1)) + \
+            self.gate(self.conv2d(x1))
+        x3 = self.conv3(x2)
+        if self.downsample is not None:
+            identity = self.downsample(identity)
+        return F.relu(x3 + identity)
+
+
+class _TorchOSNet(nn.Module):
+    def __init__(self, ch=(16, 64, 96, 128), dim=512):
+        super().__init__()
+        self.conv1, self.maxpool = _ConvLayer(3, ch[0], 7, 2, 3), nn.MaxPool2d(3, 2, 1)
+
+        def stage(i, o, trans):
+            mods = [_OSBlock(i, o), _OSBlock(o, o)]
+            if trans:
+                mods.append(nn.Sequential(_ConvLayer(o, o, 1), nn.AvgPool2d(2, 2)))
+            return nn.Sequential(*mods)
+        self.conv2, self.conv3, self.conv4 = stage(ch[0], ch[1], True), stage(ch[1], ch[2], True), stage(ch[2], ch[3], False)
+        self.conv5, self.gap = _ConvLayer(ch[3], ch[3], 1), nn.AdaptiveAvgPool2d(1)
+        self.fc = nn.Sequential(nn.Linear(ch[3], dim), nn.BatchNorm1d(dim), nn.ReLU())
+
+    def forward(self, x):
+        x = self.conv5(self.conv4(self.conv3(self.conv2(self.maxpool(self.conv1(x))))))
+        v = self.gap(x)
+        return self.fc(v.view(v.size(0), -1))
+
+
+def _torch_export(model, x, opset):
+    import io
+    import warnings
+    try:
+        from torch.onnx._internal.torchscript_exporter import onnx_proto_utils
+    except Exception:
+        pytest.skip("this torch has no TorchScript ONNX exporter")
+    # the exporter only needs the `onnx` package for custom onnxscript functions, which this graph has none of
+    keep = onnx_proto_utils._add_onnxscript_fn
+    onnx_proto_utils._add_onnxscript_fn = lambda proto, custom_opsets: proto
+    try:
+        buf = io.BytesIO()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            torch.onnx.export(model, x, buf, opset_version=opset, input_names=['images'], output_names=['features'],
+                              dynamic_axes={'images': {0: 'batch'}, 'features': {0: 'batch'}}, dynamo=False)
+        return buf.getvalue()
+    finally:
+        onnx_proto_utils._add_onnxscript_fn = keep
+
+
+@pytest.mark.parametrize("opset", [9, 11, 17])
+def test_genuine_torch_onnx_export_imports_and_matches_the_torch_forward(opset):
+    """Third-party pin of the importer: a file written by torch.onnx.export (eval-mode BN folded into the convs,
+    Shape / Gather / Concat / Reshape for the flatten, Gemm + BatchNormalization + Relu head, opset-9's zero Pad) must
+    lower to the OSNet op list and reproduce the torch module's own forward."""
+    from oracle import nets
+    torch.manual_seed(0)
+    model = _TorchOSNet().eval()
+    for mod in model.modules():
+        if isinstance(mod, (nn.BatchNorm2d, nn.BatchNorm1d)):
+            mod.running_mean.normal_(0, 0.1)
+            mod.running_var.uniform_(0.5, 2)
+            mod.weight.data.uniform_(0.5, 1.5)
+            mod.bias.data.normal_(0, 0.1)
+    x = torch.randn(2, 3, 256, 128)
+    data = _torch_export(model, x, opset)
+    g = onnx_io.parse_model(data)
+    assert g.producer == 'pytorch' and g.opset == opset
+    ops, w, in_shape, dim = import_reid_onnx(data)
+    assert in_shape == (3, 256, 128) and dim == 512
+    # the same structure as the built-in x0.25 network: the engine's fused OSBlock / stem matchers apply
+    ref_ops = osnet.build_osnet(0.25)
+    assert [o[0] for o in ops] == [o[0] for o in ref_ops]
+    assert [o[2:8] for o in ops if o[0] == 'conv'] == [o[2:8] for o in ref_ops if o[0] == 'conv']
+    with torch.no_grad():
+        want = model(x)
+    want = want / want.norm(dim=1, keepdim=True)
+    got = nets.run_osnet(ops, w, x)
+    assert float((got - want).abs().max()) < 1e-6, float((got - want).abs().max())
+
+
 def test_unsupported_nodes_raise_by_name():
     ops = osnet.build_osnet(0.25)
     w = osnet.synthetic_weights(ops, calibrate=False)
