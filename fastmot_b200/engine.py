@@ -264,9 +264,11 @@ def build_yolo_engine(model, weights=None, use_tc=True, use_graph=True, head_obj
         else:
             # FM_SYNTH_OBJ_BIAS: objectness prior of the SYNTHETIC heads (how many random-weight candidates pass
             # conf_thresh); bench.py lowers it for the big-input models so the candidate count stays realistic
+            # FM_SYNTH_HEAD_GAIN: scale of the synthetic head weights (logit variance on real frames)
             head_obj_bias = float(os.environ.get("FM_SYNTH_OBJ_BIAS", head_obj_bias))
             weights = darknet.synthetic_weights(layers, 3, head_obj_bias=head_obj_bias,
-                                                num_classes=model.NUM_CLASSES)
+                                                num_classes=model.NUM_CLASSES,
+                                                head_gain=float(os.environ.get("FM_SYNTH_HEAD_GAIN", 1.0)))
     return YoloEngine(layers, model.INPUT_SHAPE[1:], weights, use_tc=use_tc, use_graph=use_graph)
 
 

@@ -283,11 +283,13 @@ def count_flops(layers, in_c, in_h, in_w):
 
 
 # ------------------------------------------------------------------------------------------------ weights
-def synthetic_weights(layers, in_c, seed_base=1000, head_obj_bias=None, num_classes=1, calibrate=True):
+def synthetic_weights(layers, in_c, seed_base=1000, head_obj_bias=None, num_classes=1, calibrate=True, head_gain=1.0):
     """Seeded He-normal conv weights (seed = seed_base + layer index) with BN folded.
     Returns {layer_index: (weight [out][kh][kw][in] float32, bias float32[out])}.
     head_obj_bias: if set, the objectness bias of every head conv (the conv right before a [yolo] layer) is
-    initialised to it — the usual detection-prior init — so random weights give a sparse, trained-like candidate set."""
+    initialised to it — the usual detection-prior init — so random weights give a sparse, trained-like candidate set.
+    head_gain: scale of the head convs' weights after calibration (< 1 shrinks the logit variance real frames produce
+    in the deep models, so that the objectness prior, not noise, decides how many candidates pass conf_thresh)."""
     res, _ = infer_shapes(layers, in_c, 64, 64)
     out = {}
     for i, l in enumerate(res):
@@ -307,6 +309,11 @@ def synthetic_weights(layers, in_c, seed_base=1000, head_obj_bias=None, num_clas
     if calibrate:
         from .calibrate import calibrate_darknet
         out = calibrate_darknet(res, out, in_c)
+    if head_gain != 1.0:
+        for i, l in enumerate(res):
+            if l['type'] == 'convolutional' and i + 1 < len(res) and res[i + 1]['type'] == 'yolo':
+                w, b = out[i]
+                out[i] = ((w * np.float32(head_gain)).astype(np.float32), b)
     return out
 
 
