@@ -14,6 +14,8 @@ pytestmark = pytest.mark.skipif(not reference_available(), reason="reference tre
     (dict(n_objects=64, seed=1), 22),                     # config-1 size; scripted drop-outs on frames 10 / 15 -> aging,
                                                           # IoU stage and re-identification from the history
     (dict(n_objects=50, seed=7, bounce_radius=8), 31),    # direction reversals (benchmark scene motion model)
+    (dict(n_objects=30, seed=12, dropout_frames=(10,), dropout_every=1), 22),       # a detector frame with NO detections
+    (dict(n_objects=30, seed=13, dropout_frames=(5, 10, 15), dropout_every=2), 22),  # half the objects never confirm
 ])
 def test_oracle_tracker_full_pipeline_identical(scene_kw, n_frames):
     """OracleTracker + OracleFlow (cv2) vs reference MultiTracker + Flow: identical ids and boxes per frame."""
