@@ -333,3 +333,36 @@ def test_flow_runner_equals_call_by_call_sequence(monkeypatch):
         for k in ta:
             np.testing.assert_array_equal(ta[k], tb[k])
         np.testing.assert_array_equal(ba, bb)
+
+
+@pytest.mark.parametrize("scene_kw", [
+    dict(n_objects=30, seed=12, dropout_frames=(10,), dropout_every=1),        # a detector frame with NO detections
+    dict(n_objects=30, seed=13, dropout_frames=(5, 10, 15), dropout_every=2),   # half the objects never confirm
+])
+def test_tracker_edge_scenarios_vs_oracle(scene_kw):
+    """Scenarios the oracle reproduces bit-identically against the reference (tests/test_oracle_vs_reference.py):
+    the GPU tracker must show the same visible IDs every frame, boxes within +-1 px (KLT on, tier T3)."""
+    from fastmot_b200 import MultiTracker
+    from fastmot_b200.synth import SyntheticScene
+    from oracle.run import default_tracker_cfg, run_oracle_tracker
+    n_frames = 22
+    want, _ = run_oracle_tracker(SyntheticScene(**scene_kw), n_frames)
+    scene = SyntheticScene(**scene_kw)
+    trk = MultiTracker(scene.size, 'cosine', **default_tracker_cfg())
+    trk.reset(1 / 30)
+    for t in range(n_frames):
+        frame = scene.frame(t)
+        if t == 0:
+            tlbr, labels, conf, ids = scene.detections(0)
+            trk.init(frame, _dets(tlbr, labels, conf))
+        else:
+            trk.compute_flow(frame)
+            trk.apply_kalman()
+            if t % 5 == 0:
+                tlbr, labels, conf, ids = scene.detections(t)
+                trk.update(t, _dets(tlbr, labels, conf), scene.embeddings(ids, t))
+        vis = {k: v.tlbr for k, v in trk.tracks.items() if v.confirmed and v.active}
+        w = dict(zip(want[t]['ids'].tolist(), want[t]['tlbr']))
+        assert set(vis) == set(w), (t, set(vis) ^ set(w))
+        for k in vis:
+            assert np.abs(vis[k] - w[k]).max() <= 1.0, (t, k, vis[k], w[k])
