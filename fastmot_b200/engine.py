@@ -345,12 +345,6 @@ class OSNetEngine(_Net):
         self.n_osb = 0
         skip_until = -1
         pooled_by_tail = {}
-        self.n_osb = 0
-        skip_until = -1
-        pooled_by_tail = {}
-        # FM_LITE_FUSED=1: run pointwise + depthwise of each Lite 3x3 as one kernel (experimental, default off)
-        self.fuse_lite = os.environ.get("FM_LITE_FUSED", "0") == "1"
-        self.n_lite = 0
         for k, op in enumerate(self.ops):
             kind = op[0]
             if k <= skip_until:
