@@ -176,3 +176,24 @@ def test_benchmark_scene_bounce_keeps_objects_in_their_cells():
     xa, ya = bnc.positions(63)
     xb, yb = bnc.positions(64)
     assert np.abs(xb - xa).max() <= np.ceil(np.abs(bnc.vel[:, 0]).max()) + 1
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the metric, the bounded
+    sample description and the zero-copy e2e block.  Config 1 (association only) keeps it to a few seconds."""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "1",
+                        "--steps", "6", "--warmup", "2"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"].startswith("frames/sec") and d["unit"] == "frames/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 6 and d["warmup"] == 2
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "configs[0]" in d["config"]["workload"]
