@@ -418,3 +418,60 @@ def test_custom_backbone_onnx_vs_oracle_on_gpu():
     want = nets.run_osnet(ops, w, inp[..., :3].float().permute(0, 3, 1, 2), nets.fp16_roundtrip)
     assert got.shape == want.shape == (8, 24)
     assert float((got - want).abs().max()) < 5e-3, float((got - want).abs().max())
+
+
+def test_wire_codec_property_roundtrip():
+    """Randomised graphs (hypothesis): every tensor dtype / shape, attribute kind and name survives serialize -> parse."""
+    from hypothesis import given, settings, strategies as st
+    from hypothesis.extra import numpy as hnp
+    dtypes = st.sampled_from([np.float32, np.float16, np.float64, np.int64, np.int32, np.uint8, np.int8])
+    names = st.text(alphabet="abcdefghijklmnopqrstuvwxyz0123456789_./:", min_size=1, max_size=24)
+
+    @st.composite
+    def tensors(draw):
+        dt = np.dtype(draw(dtypes))
+        shape = draw(hnp.array_shapes(min_dims=0, max_dims=4, max_side=5))
+        if dt.kind == 'f':
+            elems = st.floats(-1e3, 1e3, width=16 if dt.itemsize == 2 else 32)
+        else:
+            info = np.iinfo(dt)
+            elems = st.integers(int(info.min), int(info.max))
+        return draw(hnp.arrays(dt, shape, elements=elems))
+
+    attr_vals = st.one_of(st.integers(-2**62, 2**62), st.floats(-1e6, 1e6, width=32), names,
+                          st.lists(st.integers(-2**40, 2**40), min_size=1, max_size=6),
+                          st.lists(st.floats(-1e3, 1e3, width=32), min_size=1, max_size=6), tensors())
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.dictionaries(names, tensors(), max_size=5),
+           st.lists(st.tuples(names, st.lists(names, max_size=3), st.lists(names, min_size=1, max_size=2),
+                              st.dictionaries(names, attr_vals, max_size=4)), max_size=5),
+           st.integers(1, 21), st.booleans())
+    def check(init, nodes, opset, typed):
+        g = onnx_io.Graph([onnx_io.Node(op, list(i), list(o), nm, dict(a)) for (nm, i, o, a), op in
+                           zip(nodes, ["Conv", "Relu", "Add", "Gemm", "Custom"] * 2)],
+                          dict(init), [onnx_io.ValueInfo("x", onnx_io.FLOAT, ("N", 3, 8, 8))],
+                          [onnx_io.ValueInfo("y", onnx_io.FLOAT16, (2, "M"))], opset=opset)
+        g.inputs = [v for v in g.inputs if v.name not in g.initializers]
+        g2 = onnx_io.parse_model(onnx_io.serialize(g, typed_float_data=typed))
+        assert g2.opset == opset and len(g2.nodes) == len(g.nodes)
+        for a, b in zip(g.nodes, g2.nodes):
+            assert (a.op_type, a.inputs, a.outputs, a.name) == (b.op_type, b.inputs, b.outputs, b.name)
+            assert set(a.attrs) == set(b.attrs)
+            for k, v in a.attrs.items():
+                w = b.attrs[k]
+                if isinstance(v, np.ndarray):
+                    assert w.dtype == v.dtype and w.shape == v.shape and np.array_equal(w, v, equal_nan=True)
+                elif isinstance(v, float):
+                    assert w == np.float32(v)
+                elif isinstance(v, list) and v and isinstance(v[0], float):
+                    assert w == [float(np.float32(x)) for x in v]
+                else:
+                    assert w == v, (k, v, w)
+        assert set(g2.initializers) == set(g.initializers)
+        for k, v in g.initializers.items():
+            w = g2.initializers[k]
+            assert w.dtype == v.dtype and w.shape == v.shape and np.array_equal(w, v, equal_nan=True)
+        assert [(v.name, v.elem_type, v.shape) for v in g2.outputs] == [("y", onnx_io.FLOAT16, (2, "M"))]
+
+    check()
