@@ -442,7 +442,7 @@ def test_wire_codec_property_roundtrip():
                           st.lists(st.integers(-2**40, 2**40), min_size=1, max_size=6),
                           st.lists(st.floats(-1e3, 1e3, width=32), min_size=1, max_size=6), tensors())
 
-    @settings(max_examples=60, deadline=None)
+    @settings(max_examples=60, deadline=None, derandomize=True, database=None)
     @given(st.dictionaries(names, tensors(), max_size=5),
            st.lists(st.tuples(names, st.lists(names, max_size=3), st.lists(names, min_size=1, max_size=2),
                               st.dictionaries(names, attr_vals, max_size=4)), max_size=5),
